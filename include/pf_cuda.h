@@ -1,0 +1,207 @@
+/*
+ * pf_cuda.h -- C ABI of libpf_cuda.so: the B200 (sm_100a) engine for SimPEG's
+ * integral-equation potential-field hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI on this path: the
+ * hot loops are numba-jitted Python functions selected through the dict
+ * NUMBA_FUNCTIONS_3D and called from four private methods of
+ * gravity.Simulation3DIntegral / magnetics.Simulation3DIntegral.  Each entry
+ * point below names the reference function(s) it replaces (paths relative to
+ * the reference root, simpeg/potential_fields/...).  INTEGRATION.md shows the
+ * ctypes binding a SimPEG maintainer would add for engine="cuda".
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative pf_status otherwise; the
+ *    message of the last error of the calling thread is pf_last_error();
+ *  - nothing throws or exits across the ABI;
+ *  - all array pointers are DEVICE pointers owned by the caller (torch
+ *    tensors on the host side); the library allocates nothing that outlives a
+ *    call; scratch memory is passed in as `workspace` (size from the matching
+ *    *_workspace_bytes query);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - all arithmetic is IEEE fp64; G may be stored as fp64 or fp32
+ *    (sensitivity_dtype, base.py:196-215).
+ */
+#ifndef PF_CUDA_H
+#define PF_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+typedef enum {
+    PF_OK = 0,
+    PF_ERR_INVALID = -1,     /* bad argument (null pointer, bad enum, bad size) */
+    PF_ERR_UNSUPPORTED = -2, /* component set not supported on this physics      */
+    PF_ERR_WORKSPACE = -3,   /* workspace too small                              */
+    PF_ERR_CUDA = -4         /* CUDA runtime error (message has the cudaError)   */
+} pf_status;
+
+/* Component codes.  Gravity: gravity/receivers.py:56-71 and the kernel table
+ * gravity/simulation.py:74-85.  Magnetics: magnetics/receivers.py:46-62 and
+ * magnetics/simulation.py:29-103 (CHOCLO_SUPPORTED_COMPONENTS). */
+typedef enum {
+    PF_GX = 0, PF_GY = 1, PF_GZ = 2,
+    PF_GXX = 3, PF_GYY = 4, PF_GZZ = 5, PF_GXY = 6, PF_GXZ = 7, PF_GYZ = 8,
+    PF_GUV = 9,
+    PF_TMI = 16, PF_BX = 17, PF_BY = 18, PF_BZ = 19,
+    PF_BXX = 20, PF_BYY = 21, PF_BZZ = 22, PF_BXY = 23, PF_BXZ = 24, PF_BYZ = 25,
+    PF_TMI_X = 26, PF_TMI_Y = 27, PF_TMI_Z = 28
+} pf_component;
+
+typedef enum { PF_GRAVITY = 0, PF_MAGNETICS = 1 } pf_physics;
+typedef enum { PF_F64 = 0, PF_F32 = 1 } pf_dtype;
+
+#define PF_MAX_COMPONENTS 16
+
+/*
+ * Tile plan: the device-resident form of what the reference obtains from
+ * BasePFSimulation._get_active_nodes() (base.py:371-399): the active nodes
+ * and the (nC, 8) cell -> node table.  Active cells are partitioned into
+ * tiles of at most `tile_cells` cells whose union of vertices has at most
+ * `tile_nodes` nodes; a CTA evaluates the prism kernels once per (receiver,
+ * tile node) in shared memory and combines them per cell (the same
+ * node-sharing the reference gets from its per-receiver `kernels` array,
+ * gravity/_numba/_3d_mesh.py:147-163).
+ */
+typedef struct {
+    int64_t n_tiles;
+    int64_t n_cells;               /* nC: active cells = columns per block of G */
+    int32_t tile_cells;            /* TC: slots per tile (multiple of 256)      */
+    int32_t tile_nodes;            /* TN: node slots per tile (multiple of 256) */
+    const double *tile_xyz;        /* [n_tiles][3][TN] node coordinates (SoA)   */
+    const uint16_t *tile_cell_nodes; /* [n_tiles][TC][8] local node ids, F-order  */
+    const int32_t *tile_cell_col;  /* [n_tiles][TC] global cell index, -1 = pad */
+    const int32_t *tile_n_nodes;   /* [n_tiles] nodes used in each tile         */
+} pf_plan;
+
+/*
+ * One receiver object = one (components, locations) pair of
+ * BasePFSimulation._get_components_and_receivers() (base.py:401-408).
+ * Rows are location-major, component-minor:
+ *     row = row_offset + i_location * n_components + i_component
+ * (vector_slice / matrix_slice of gravity/simulation.py:570-572, 617-619).
+ */
+typedef struct {
+    int32_t physics;               /* pf_physics */
+    int32_t n_components;
+    int32_t components[PF_MAX_COMPONENTS]; /* pf_component, in receiver order */
+    int32_t scalar_model;          /* magnetics: 1 = scalar chi, 0 = vector (3 nC columns) */
+    int32_t reserved;
+    double b0[3];                  /* magnetics: inducing field (survey.source_field.b0)   */
+    const double *receivers;       /* [n_receivers][3] (x, y, z), device                   */
+    int64_t n_receivers;
+    int64_t row_offset;            /* first row of this object in G / dpred / v / w        */
+} pf_job;
+
+int pf_abi_version(void);
+const char *pf_last_error(void);
+
+/* number of columns of G for a job: nC (gravity, scalar) or 3 nC (vector) */
+int64_t pf_job_columns(const pf_plan *plan, const pf_job *job);
+
+/*
+ * pf_build_G -- fill the rows of G that belong to one receiver object.
+ * Replaces: _sensitivity_gravity (gravity/_numba/_3d_mesh.py:97-163) as
+ * dispatched by gravity/simulation.py:585-629, and _sensitivity_mag /
+ * _sensitivity_tmi / _sensitivity_tmi_derivative
+ * (magnetics/_numba/_3d_mesh.py:21-557) as dispatched by
+ * magnetics/simulation.py:931-1026.  All components of the object are produced
+ * in one pass.  G is row-major with leading dimension ldG (elements).
+ */
+int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64_t ldG,
+               int g_dtype, void *stream);
+
+/*
+ * pf_forward -- fields[row] += sum_k G[row,k] * model[k] without storing G
+ * (store_sensitivities="forward_only").
+ * Replaces: _forward_gravity (gravity/_numba/_3d_mesh.py:21-94; dispatch
+ * gravity/simulation.py:541-583) and _forward_mag/_forward_tmi/
+ * _forward_tmi_derivative (magnetics/_numba/_3d_mesh.py:1913-2360; dispatch
+ * magnetics/simulation.py:829-929).  `fields` is the full (nD,) vector and is
+ * accumulated into, like the reference.
+ */
+int64_t pf_forward_workspace_bytes(const pf_plan *plan, const pf_job *job);
+int pf_forward(const pf_plan *plan, const pf_job *job, const double *model,
+               double *fields, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * pf_gt_dot_v -- result[k] += sum_rows G[row,k] * v[row] without storing G.
+ * Replaces: _sensitivity_gravity_t_dot_v_{serial,parallel}
+ * (gravity/_numba/_3d_mesh.py:320-469; dispatch gravity/simulation.py:631-671)
+ * and _{mag,tmi,tmi_derivative}_sensitivity_t_dot_v_*
+ * (magnetics/_numba/_3d_mesh.py:560-1273; dispatch magnetics/simulation.py:
+ * 1046-1141).  `v` is the full (nD,) vector.
+ */
+int64_t pf_gt_dot_v_workspace_bytes(const pf_plan *plan, const pf_job *job);
+int pf_gt_dot_v(const pf_plan *plan, const pf_job *job, const double *v,
+                double *result, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * pf_gtg_diag -- diag[k] += sum_rows w[row] * G[row,k]^2 without storing G.
+ * Replaces: _diagonal_G_T_dot_G_{serial,parallel}
+ * (gravity/_numba/_3d_mesh.py:166-317; dispatch gravity/simulation.py:690-724)
+ * and _diagonal_G_T_dot_G_{mag,tmi,tmi_deriv}_* (magnetics/_numba/_3d_mesh.py:
+ * 1276-1910; dispatch magnetics/simulation.py:1143-1232).  `w` is the full
+ * (nD,) vector of squared data weights and is indexed by ROW (the reference
+ * indexes it by receiver, which is only right for one-component objects; the
+ * stored-G definition np.einsum("i,ij,ij->j", w, G, G), gravity/simulation.py:
+ * 313-315, is what this implements).
+ */
+int64_t pf_gtg_diag_workspace_bytes(const pf_plan *plan, const pf_job *job);
+int pf_gtg_diag(const pf_plan *plan, const pf_job *job, const double *w,
+                double *diag, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * Stored-G products (store_sensitivities="ram").  G is rows x cols, row-major,
+ * leading dimension ld, dtype fp64 or fp32; vectors are fp64; accumulation is
+ * fp64.  Replace the numpy/BLAS expressions
+ *   pf_gemv      y = G @ x        gravity/simulation.py:220,387  magnetics/simulation.py:252,489,540
+ *   pf_gemv_t    z = G.T @ y      gravity/simulation.py:418      magnetics/simulation.py:533
+ *   pf_colsumsq  d = einsum("i,ij,ij->j", w, G, G)   gravity/simulation.py:313-315  magnetics/simulation.py:441-443
+ * All three OVERWRITE their output.
+ */
+int64_t pf_gemv_workspace_bytes(int64_t rows, int64_t cols);
+int pf_gemv(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
+            const double *x, double *y, void *workspace, int64_t workspace_bytes,
+            void *stream);
+int64_t pf_gemv_t_workspace_bytes(int64_t rows, int64_t cols);
+int pf_gemv_t(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
+              const double *y, double *z, void *workspace, int64_t workspace_bytes,
+              void *stream);
+int pf_colsumsq(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
+                const double *w, double *d, void *workspace, int64_t workspace_bytes,
+                void *stream);
+
+/*
+ * Amplitude data (is_amplitude_data=True, magnetics/simulation.py:444-456,
+ * 491-495, 529-565).  Rows come in (bx, by, bz) triplets per location.
+ *   pf_amp_normalize   amp[i] = |B_i|, ampderiv[c][i] = B_i[c] / |B_i|   (normalized_fields, 546-565)
+ *   pf_amp_combine     out[i] = sum_c ampderiv[c][i] * jv[3 i + c]       (Jvec, 491-495)
+ *   pf_amp_spread      out[3 i + c] = ampderiv[c][i] * v[i]              (Jtvec, 529-532)
+ *   pf_colsumsq_amp    d[k] = sum_i w[i] (sum_c ampderiv[c][i] G[3i+c,k])^2   (444-456)
+ * ampderiv is stored (3, n_loc) row-major like the reference's array.
+ */
+int pf_amp_normalize(const double *b_xyz, int64_t n_loc, double *amp, double *ampderiv,
+                     void *stream);
+int pf_amp_combine(const double *ampderiv, const double *jv, int64_t n_loc, double *out,
+                   void *stream);
+int pf_amp_spread(const double *ampderiv, const double *v, int64_t n_loc, double *out,
+                  void *stream);
+int pf_colsumsq_amp(const void *G, int64_t n_loc, int64_t cols, int64_t ld, int g_dtype,
+                    const double *w, const double *ampderiv, double *d, void *workspace,
+                    int64_t workspace_bytes, void *stream);
+
+/* FP64 pipe peak probe: runs a dependent-free DFMA loop and returns the
+ * achieved FLOP/s (2 per DFMA) in *flops; used by bench.py for the roofline
+ * denominator of the compute-bound build kernels. */
+int pf_probe_fp64_peak(double *flops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_CUDA_H */

@@ -1,0 +1,297 @@
+"""
+Device-side engine: owns the torch buffers (tile plan, receivers, G, scratch)
+and issues the C-ABI calls of ``libpf_cuda.so`` on the current CUDA stream.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in
+the hand-written sm_100a kernels behind ``include/pf_cuda.h``.
+
+The engine works on the LOCAL receiver shard of this process (see
+``simpeg_b200/sharding.py``); rows are local rows.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .tiling import TILE_CELLS, TILE_NODES, TilePlan, build_tile_plan
+
+_G_ALIGN = 16  # leading dimension of G in elements (128 B rows for fp64)
+
+
+def _require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "engine='cuda' requires a CUDA device (no CPU fallback): "
+            "torch.cuda.is_available() is False"
+        )
+    return torch
+
+
+class CudaEngine:
+    """
+    Parameters
+    ----------
+    physics : "gravity" | "magnetics"
+    nodes, cell_nodes : active nodes (nN, 3) and cell -> node table (nC, 8)
+    receiver_list : list of (locations (R, 3), components list[str]) -- LOCAL shard
+    b0 : (3,) inducing field for magnetics
+    model_type : "scalar" | "vector"
+    sensitivity_dtype : np.float64 | np.float32 (storage of G)
+    device : torch device / index (default: current device)
+    """
+
+    def __init__(self, physics, nodes, cell_nodes, receiver_list, b0=None,
+                 model_type="scalar", sensitivity_dtype=np.float64, device=None,
+                 plan: TilePlan | None = None):
+        torch = _require_cuda()
+        self.torch = torch
+        self.lib = _lib.load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        if physics not in ("gravity", "magnetics"):
+            raise ValueError(f"unknown physics {physics!r}")
+        self.physics = physics
+        self.scalar = (model_type == "scalar")
+        if sensitivity_dtype not in (np.float64, np.float32):
+            raise TypeError("sensitivity_dtype must be np.float32 or np.float64")
+        self.g_dtype = sensitivity_dtype
+        self._g_code = _lib.PF_F64 if sensitivity_dtype is np.float64 else _lib.PF_F32
+        self._g_torch = torch.float64 if sensitivity_dtype is np.float64 else torch.float32
+
+        self.host_plan = plan if plan is not None else build_tile_plan(nodes, cell_nodes)
+        hp = self.host_plan
+        self.nC = hp.n_cells
+        self.nblk = 1 if (physics == "gravity" or self.scalar) else 3
+        self.nP = self.nC * self.nblk
+        with torch.cuda.device(self.device):
+            self._t_xyz = torch.from_numpy(hp.tile_xyz).to(self.device)
+            # torch has no uint16 arithmetic; the bytes are only ever read by the kernel
+            self._t_cn = torch.from_numpy(hp.tile_cell_nodes.view(np.int16)).to(self.device)
+            self._t_col = torch.from_numpy(hp.tile_cell_col).to(self.device)
+            self._t_nn = torch.from_numpy(hp.tile_n_nodes).to(self.device)
+        self.plan = _lib.PfPlan(
+            n_tiles=hp.n_tiles, n_cells=hp.n_cells, tile_cells=TILE_CELLS, tile_nodes=TILE_NODES,
+            tile_xyz=self._t_xyz.data_ptr(), tile_cell_nodes=self._t_cn.data_ptr(),
+            tile_cell_col=self._t_col.data_ptr(), tile_n_nodes=self._t_nn.data_ptr())
+
+        table = _lib.GRAVITY_COMPONENTS if physics == "gravity" else _lib.MAGNETIC_COMPONENTS
+        code = _lib.PF_GRAVITY if physics == "gravity" else _lib.PF_MAGNETICS
+        b0 = np.zeros(3) if b0 is None else np.asarray(b0, dtype=np.float64).reshape(3)
+        self.jobs = []
+        self._rx = []
+        offset = 0
+        for locations, components in receiver_list:
+            components = [components] if isinstance(components, str) else list(components)
+            unknown = [c for c in components if c not in table]
+            if unknown:
+                raise NotImplementedError(
+                    f"Other components besides {set(table)} aren't implemented yet "
+                    f"(got {unknown}).")
+            if len(components) > _lib.PF_MAX_COMPONENTS:
+                raise ValueError("too many components in one receiver object")
+            loc = np.ascontiguousarray(locations, dtype=np.float64).reshape(-1, 3)
+            rx = torch.from_numpy(loc).to(self.device)
+            self._rx.append(rx)
+            job = _lib.PfJob()
+            job.physics = code
+            job.n_components = len(components)
+            for i, c in enumerate(components):
+                job.components[i] = table[c]
+            job.scalar_model = int(self.scalar)
+            job.b0[:] = list(b0)
+            job.receivers = rx.data_ptr() if loc.shape[0] else None
+            job.n_receivers = loc.shape[0]
+            job.row_offset = offset
+            self.jobs.append(job)
+            offset += loc.shape[0] * len(components)
+        self.n_rows = offset
+        self.G = None
+        self.ld = 0
+        self._ws = None
+        self.launches = 0  # kernels launched through the C ABI (bench bookkeeping)
+
+    # ------------------------------------------------------------------ utils
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, nbytes):
+        nbytes = max(int(nbytes), 8)
+        if self._ws is None or self._ws.numel() * 8 < nbytes:
+            self._ws = None
+            self._ws = self.torch.empty((nbytes + 7) // 8, dtype=self.torch.float64, device=self.device)
+        return self._ws
+
+    def to_device(self, array, n=None):
+        a = np.ascontiguousarray(array, dtype=np.float64).reshape(-1)
+        if n is not None and a.shape[0] != n:
+            raise ValueError(f"expected a vector of length {n}, got {a.shape[0]}")
+        return self.torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    @staticmethod
+    def to_host(tensor):
+        return tensor.detach().cpu().numpy()
+
+    def _jp(self, job):
+        return ctypes.byref(self.plan), ctypes.byref(job)
+
+    # ----------------------------------------------------------- build / sinks
+    def build_G(self):
+        """Fill the local block of G on the device (rows_local x nP, row-major)."""
+        torch = self.torch
+        self.ld = -(-max(self.nP, 1) // _G_ALIGN) * _G_ALIGN
+        with torch.cuda.device(self.device):
+            if self.G is None:
+                self.G = torch.empty((self.n_rows, self.ld), dtype=self._g_torch, device=self.device)
+            for job in self.jobs:
+                _lib.check(self.lib.pf_build_G(*self._jp(job), self.G.data_ptr(), self.ld,
+                                               self._g_code, self._stream()), "pf_build_G")
+                self.launches += 1
+        return self.G
+
+    def forward_dev(self, model_t, out=None):
+        """fields = G_local @ model without storing G (device tensors)."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            fields = torch.zeros(self.n_rows, dtype=torch.float64, device=self.device) if out is None \
+                else out.zero_()
+            for job in self.jobs:
+                nbytes = self.lib.pf_forward_workspace_bytes(*self._jp(job))
+                ws = self._workspace(nbytes)
+                _lib.check(self.lib.pf_forward(*self._jp(job), model_t.data_ptr(), fields.data_ptr(),
+                                               ws.data_ptr(), ws.numel() * 8, self._stream()),
+                           "pf_forward")
+                self.launches += 2
+        return fields
+
+    def _column_sink(self, fn, wsfn, vec_t, name, out=None):
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            result = torch.zeros(self.nP, dtype=torch.float64, device=self.device) if out is None \
+                else out.zero_()
+            for job in self.jobs:
+                nbytes = wsfn(*self._jp(job))
+                ws = self._workspace(nbytes)
+                _lib.check(fn(*self._jp(job), vec_t.data_ptr(), result.data_ptr(), ws.data_ptr(),
+                              ws.numel() * 8, self._stream()), name)
+                self.launches += 2
+        return result
+
+    def gt_dot_v_dev(self, v_t, out=None):
+        """G_local.T @ v_local without storing G."""
+        return self._column_sink(self.lib.pf_gt_dot_v, self.lib.pf_gt_dot_v_workspace_bytes, v_t,
+                                 "pf_gt_dot_v", out)
+
+    def gtg_diag_dev(self, w_t, out=None):
+        """sum_rows w[row] G_local[row, :]**2 without storing G."""
+        return self._column_sink(self.lib.pf_gtg_diag, self.lib.pf_gtg_diag_workspace_bytes, w_t,
+                                 "pf_gtg_diag", out)
+
+    # ------------------------------------------------------- stored-G products
+    def _need_G(self):
+        if self.G is None:
+            self.build_G()
+        return self.G
+
+    def gemv_dev(self, x_t, out=None):
+        torch = self.torch
+        G = self._need_G()
+        with torch.cuda.device(self.device):
+            y = torch.empty(self.n_rows, dtype=torch.float64, device=self.device) if out is None else out
+            ws = self._workspace(self.lib.pf_gemv_workspace_bytes(self.n_rows, self.nP))
+            _lib.check(self.lib.pf_gemv(G.data_ptr(), self.n_rows, self.nP, self.ld, self._g_code,
+                                        x_t.data_ptr(), y.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                        self._stream()), "pf_gemv")
+            self.launches += 2
+        return y
+
+    def gemv_t_dev(self, y_t, out=None):
+        torch = self.torch
+        G = self._need_G()
+        with torch.cuda.device(self.device):
+            z = torch.empty(self.nP, dtype=torch.float64, device=self.device) if out is None else out
+            ws = self._workspace(self.lib.pf_gemv_t_workspace_bytes(self.n_rows, self.nP))
+            _lib.check(self.lib.pf_gemv_t(G.data_ptr(), self.n_rows, self.nP, self.ld, self._g_code,
+                                          y_t.data_ptr(), z.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                          self._stream()), "pf_gemv_t")
+            self.launches += 2
+        return z
+
+    def colsumsq_dev(self, w_t, out=None):
+        torch = self.torch
+        G = self._need_G()
+        with torch.cuda.device(self.device):
+            d = torch.empty(self.nP, dtype=torch.float64, device=self.device) if out is None else out
+            ws = self._workspace(self.lib.pf_gemv_t_workspace_bytes(self.n_rows, self.nP))
+            _lib.check(self.lib.pf_colsumsq(G.data_ptr(), self.n_rows, self.nP, self.ld, self._g_code,
+                                            w_t.data_ptr(), d.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                            self._stream()), "pf_colsumsq")
+            self.launches += 2
+        return d
+
+    # --------------------------------------------------------------- amplitude
+    def amp_normalize_dev(self, b_t):
+        """(amplitude (n_loc,), ampderiv (3, n_loc)) of interleaved (bx,by,bz) rows."""
+        torch = self.torch
+        n_loc = b_t.numel() // 3
+        with torch.cuda.device(self.device):
+            amp = torch.empty(n_loc, dtype=torch.float64, device=self.device)
+            ad = torch.empty((3, n_loc), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.pf_amp_normalize(b_t.data_ptr(), n_loc, amp.data_ptr(), ad.data_ptr(),
+                                                 self._stream()), "pf_amp_normalize")
+            self.launches += 1
+        return amp, ad
+
+    def amp_combine_dev(self, ad_t, jv_t):
+        torch = self.torch
+        n_loc = ad_t.shape[1]
+        with torch.cuda.device(self.device):
+            out = torch.empty(n_loc, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.pf_amp_combine(ad_t.data_ptr(), jv_t.data_ptr(), n_loc, out.data_ptr(),
+                                               self._stream()), "pf_amp_combine")
+            self.launches += 1
+        return out
+
+    def amp_spread_dev(self, ad_t, v_t):
+        torch = self.torch
+        n_loc = ad_t.shape[1]
+        with torch.cuda.device(self.device):
+            out = torch.empty(3 * n_loc, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.pf_amp_spread(ad_t.data_ptr(), v_t.data_ptr(), n_loc, out.data_ptr(),
+                                              self._stream()), "pf_amp_spread")
+            self.launches += 1
+        return out
+
+    def colsumsq_amp_dev(self, w_t, ad_t):
+        torch = self.torch
+        G = self._need_G()
+        n_loc = self.n_rows // 3
+        with torch.cuda.device(self.device):
+            d = torch.empty(self.nP, dtype=torch.float64, device=self.device)
+            ws = self._workspace(self.lib.pf_gemv_t_workspace_bytes(n_loc, self.nP))
+            _lib.check(self.lib.pf_colsumsq_amp(G.data_ptr(), n_loc, self.nP, self.ld, self._g_code,
+                                                w_t.data_ptr(), ad_t.data_ptr(), d.data_ptr(),
+                                                ws.data_ptr(), ws.numel() * 8, self._stream()),
+                       "pf_colsumsq_amp")
+            self.launches += 2
+        return d
+
+    def G_to_numpy(self):
+        """Copy the local block of G to the host (small problems / tests only)."""
+        G = self._need_G()
+        return G[:, : self.nP].cpu().numpy()
+
+
+def probe_fp64_peak(device=None):
+    """Measured FP64 FMA-pipe peak in FLOP/s (roofline denominator of the build)."""
+    torch = _require_cuda()
+    lib = _lib.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.pf_probe_fp64_peak(ctypes.byref(out), stream), "pf_probe_fp64_peak")
+    return float(out.value)

@@ -1,0 +1,237 @@
+"""
+Tile planner: host-side preparation of the mesh for the CUDA kernels.
+
+The reference evaluates the prism kernels once per *unique active node* and
+gathers 8 values per cell through ``cell_nodes``
+(``BasePFSimulation._get_active_nodes``, base.py:371-399, consumed by
+gravity/_numba/_3d_mesh.py:147-163).  On the GPU the same node sharing is done
+at tile granularity: active cells are partitioned into compact tiles of at
+most ``TILE_CELLS`` cells whose vertices are at most ``TILE_NODES`` distinct
+nodes, so that one CTA can keep the per-receiver node kernel values of a tile
+in shared memory.
+
+Two partitioners:
+
+* tensor-like meshes (every active cell has a distinct integer (ix, iy, iz)
+  position on the grid of unique cell-centre coordinates; inactive cells
+  allowed): axis-aligned bricks whose dimensions are chosen to minimise the
+  number of tiles;
+* anything else (TreeMesh with hanging nodes, arbitrary cell_nodes tables):
+  recursive coordinate bisection with cuts placed between distinct centre
+  coordinates, until both limits hold.
+
+The cell order inside G is untouched: every tile slot records the original
+(active) cell index as its G column.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+TILE_CELLS = 512
+TILE_NODES = 768
+_ROUND = 256  # threads per CTA: cost is paid per round of 256 nodes / cells
+
+
+@dataclass
+class TilePlan:
+    """Host arrays of the tile plan (see include/pf_cuda.h ``pf_plan``)."""
+
+    n_tiles: int
+    n_cells: int
+    tile_xyz: np.ndarray         # (n_tiles, 3, TILE_NODES) float64
+    tile_cell_nodes: np.ndarray  # (n_tiles, TILE_CELLS, 8) uint16
+    tile_cell_col: np.ndarray    # (n_tiles, TILE_CELLS) int32, -1 = padding
+    tile_n_nodes: np.ndarray     # (n_tiles,) int32
+    method: str = ""
+
+    @property
+    def node_evaluations(self) -> int:
+        """(receiver-independent) number of node kernel evaluations per receiver"""
+        return int(self.tile_n_nodes.sum())
+
+    @property
+    def nodes_per_cell(self) -> float:
+        return self.node_evaluations / max(self.n_cells, 1)
+
+
+def _cell_centers(nodes, cell_nodes):
+    centers = np.empty((cell_nodes.shape[0], 3))
+    for ax in range(3):
+        centers[:, ax] = nodes[:, ax][cell_nodes].mean(axis=1)
+    return centers
+
+
+def _tile_cost(n_cells, n_nodes):
+    # rounds of 256 threads; a node round costs ~4x a cell round (atan/log vs adds)
+    return 4 * -(-n_nodes // _ROUND) + -(-n_cells // _ROUND)
+
+
+def _brick_tile_ids(centers):
+    """Brick decomposition for tensor-like meshes, or None."""
+    n = centers.shape[0]
+    idx = []
+    dims = []
+    for ax in range(3):
+        u, inv = np.unique(centers[:, ax], return_inverse=True)
+        idx.append(inv.astype(np.int64))
+        dims.append(len(u))
+    if dims[0] * dims[1] * dims[2] < n or dims[0] * dims[1] * dims[2] > 8 * n + 4096:
+        return None
+    lin = idx[0] + dims[0] * (idx[1] + dims[1] * idx[2])
+    if len(np.unique(lin)) != n:
+        return None
+    best = None
+    for bx in range(1, 17):
+        for by in range(1, 17):
+            for bz in range(1, 17):
+                if bx * by * bz > TILE_CELLS or (bx + 1) * (by + 1) * (bz + 1) > TILE_NODES:
+                    continue
+                cost = 0
+                # full and remainder bricks along every axis
+                parts = []
+                for d, b in zip(dims, (bx, by, bz)):
+                    full, rem = divmod(d, b)
+                    parts.append([(b, full)] + ([(rem, 1)] if rem else []))
+                for sx, cx in parts[0]:
+                    for sy, cy in parts[1]:
+                        for sz, cz in parts[2]:
+                            cost += cx * cy * cz * _tile_cost(sx * sy * sz, (sx + 1) * (sy + 1) * (sz + 1))
+                key = (cost, -bx)  # prefer long x runs (contiguous G columns)
+                if best is None or key < best[0]:
+                    best = (key, (bx, by, bz))
+    bx, by, bz = best[1]
+    nbx, nby = -(-dims[0] // bx), -(-dims[1] // by)
+    tile = (idx[0] // bx) + nbx * ((idx[1] // by) + nby * (idx[2] // bz))
+    return tile
+
+
+def _rcb_tile_ids(centers, cell_nodes):
+    """Recursive coordinate bisection with cuts between distinct coordinates."""
+    n = centers.shape[0]
+    tile = np.zeros(n, dtype=np.int64)
+    next_id = 1
+    stack = [np.arange(n)]
+    done = []
+    while stack:
+        ids = stack.pop()
+        if len(ids) <= TILE_CELLS and len(np.unique(cell_nodes[ids])) <= TILE_NODES:
+            done.append(ids)
+            continue
+        c = centers[ids]
+        ext = c.max(axis=0) - c.min(axis=0)
+        split = None
+        for ax in np.argsort(-ext):
+            vals = c[:, ax]
+            u = np.unique(vals)
+            if len(u) < 2:
+                continue
+            # cut between distinct coordinates, as close to the median as possible
+            med = np.median(vals)
+            cuts = 0.5 * (u[:-1] + u[1:])
+            cut = cuts[np.argmin(np.abs(cuts - med))]
+            left = vals < cut
+            split = (ids[left], ids[~left])
+            break
+        if split is None:
+            # all centres coincide (degenerate); split by count
+            h = len(ids) // 2
+            split = (ids[:h], ids[h:])
+        stack.extend(split)
+    for k, ids in enumerate(done):
+        tile[ids] = k
+    del next_id
+    return tile
+
+
+def _enforce_limits(tile, centers, cell_nodes):
+    """Split any tile that exceeds the cell or node limits (RCB on that tile)."""
+    counts = np.bincount(tile)
+    order = np.argsort(tile, kind="stable")
+    starts = np.r_[0, np.cumsum(counts)]
+    next_id = len(counts)
+    for t in range(len(counts)):
+        ids = order[starts[t]:starts[t + 1]]
+        if len(ids) == 0:
+            continue
+        if len(ids) <= TILE_CELLS and len(np.unique(cell_nodes[ids])) <= TILE_NODES:
+            continue
+        sub = _rcb_tile_ids(centers[ids], cell_nodes[ids])
+        sub_new = np.where(sub == 0, t, next_id + sub - 1)
+        tile[ids] = sub_new
+        next_id += int(sub.max())
+    # compact ids
+    _, tile = np.unique(tile, return_inverse=True)
+    return tile.astype(np.int64)
+
+
+def build_tile_plan(nodes, cell_nodes, method="auto") -> TilePlan:
+    """
+    Parameters
+    ----------
+    nodes : (nN, 3) float array -- active node locations
+    cell_nodes : (nC, 8) int array -- node indices of every active cell, F-order
+    method : "auto" | "brick" | "rcb"
+    """
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    cell_nodes = np.ascontiguousarray(cell_nodes, dtype=np.int64)
+    if nodes.ndim != 2 or nodes.shape[1] != 3:
+        raise ValueError(f"nodes must be (nN, 3), got {nodes.shape}")
+    if cell_nodes.ndim != 2 or cell_nodes.shape[1] != 8:
+        raise ValueError(f"cell_nodes must be (nC, 8), got {cell_nodes.shape}")
+    n_cells = cell_nodes.shape[0]
+    n_nodes = nodes.shape[0]
+    if n_cells and (cell_nodes.min() < 0 or cell_nodes.max() >= n_nodes):
+        raise ValueError("cell_nodes holds indices outside the nodes array")
+    if n_cells >= 2**31:
+        raise ValueError("more than 2^31-1 active cells are not supported")
+    if n_cells == 0:
+        return TilePlan(0, 0, np.zeros((0, 3, TILE_NODES)), np.zeros((0, TILE_CELLS, 8), np.uint16),
+                        np.zeros((0, TILE_CELLS), np.int32), np.zeros(0, np.int32), "empty")
+
+    centers = _cell_centers(nodes, cell_nodes)
+    tile = None
+    used = method
+    if method in ("auto", "brick"):
+        tile = _brick_tile_ids(centers)
+        used = "brick"
+        if tile is None and method == "brick":
+            raise ValueError("mesh is not tensor-like; use method='rcb'")
+    if tile is None:
+        tile = _rcb_tile_ids(centers, cell_nodes)
+        used = "rcb"
+    _, tile = np.unique(tile, return_inverse=True)  # compact (bricks may be empty)
+    tile = _enforce_limits(tile.astype(np.int64), centers, cell_nodes)
+    n_tiles = int(tile.max()) + 1
+
+    # ---- cells: slots ordered by original index inside each tile -------------
+    order = np.argsort(tile, kind="stable")  # stable: ascending column inside a tile
+    counts = np.bincount(tile, minlength=n_tiles)
+    starts = np.r_[0, np.cumsum(counts)[:-1]]
+    pos = np.arange(n_cells) - np.repeat(starts, counts)
+    slot = tile[order] * TILE_CELLS + pos
+    tile_cell_col = np.full(n_tiles * TILE_CELLS, -1, dtype=np.int32)
+    tile_cell_col[slot] = order.astype(np.int32)
+
+    # ---- nodes: unique (tile, node) pairs, local ids in ascending node order ---
+    key = (tile[:, None] * np.int64(n_nodes) + cell_nodes).ravel()
+    ukey, inv = np.unique(key, return_inverse=True)
+    utile = ukey // n_nodes
+    unode = ukey - utile * n_nodes
+    ncounts = np.bincount(utile, minlength=n_tiles)
+    if ncounts.max() > TILE_NODES or counts.max() > TILE_CELLS:
+        raise RuntimeError("tile planner produced an oversized tile")  # pragma: no cover
+    nstarts = np.r_[0, np.cumsum(ncounts)[:-1]]
+    local = (inv - nstarts[utile[inv]]).reshape(n_cells, 8)
+    tile_cell_nodes = np.zeros((n_tiles * TILE_CELLS, 8), dtype=np.uint16)
+    tile_cell_nodes[slot] = local[order].astype(np.uint16)
+    npos = np.arange(len(ukey)) - np.repeat(nstarts, ncounts)
+    tile_xyz = np.zeros((n_tiles, 3, TILE_NODES), dtype=np.float64)
+    for ax in range(3):
+        tile_xyz[utile, ax, npos] = nodes[unode, ax]
+
+    return TilePlan(n_tiles, n_cells, tile_xyz,
+                    tile_cell_nodes.reshape(n_tiles, TILE_CELLS, 8),
+                    tile_cell_col.reshape(n_tiles, TILE_CELLS),
+                    ncounts.astype(np.int32), used)
