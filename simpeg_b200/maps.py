@@ -1,0 +1,42 @@
+"""
+Minimal model mappings (the two the reference's hot-path tests use:
+``maps.IdentityMap`` and ``maps.ExpMap``).  Mappings stay on the host; their
+(sparse) derivatives are applied before / after the device calls, exactly as
+in the reference (gravity/simulation.py:386-387, 418-419).  Any object with
+``__mul__(m)`` and ``deriv(m)`` (e.g. a real ``simpeg.maps`` mapping) works.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+
+class IdentityMap:
+    def __init__(self, mesh=None, nP=None):
+        if nP is None and mesh is not None:
+            nP = mesh.n_cells
+        self.nP = nP
+
+    @property
+    def shape(self):
+        return (self.nP, self.nP)
+
+    def _transform(self, m):
+        return np.asarray(m, dtype=np.float64)
+
+    def __mul__(self, m):
+        return self._transform(m)
+
+    def deriv(self, m, v=None):
+        n = self.nP if self.nP is not None else np.asarray(m).size
+        d = sp.identity(n, format="csr")
+        return d if v is None else d @ v
+
+
+class ExpMap(IdentityMap):
+    def _transform(self, m):
+        return np.exp(np.asarray(m, dtype=np.float64))
+
+    def deriv(self, m, v=None):
+        d = sp.diags(np.exp(np.asarray(m, dtype=np.float64)), format="csr")
+        return d if v is None else d @ v

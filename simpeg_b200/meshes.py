@@ -1,0 +1,217 @@
+"""
+Minimal numpy meshes exposing the attributes the potential-field simulations
+read from ``discretize`` meshes (``discretize`` is not a dependency here):
+
+    dim, n_cells, n_nodes, nodes, cell_nodes, cell_centers, shape_cells,
+    shape_nodes (TensorMesh) / total_nodes (TreeMesh)
+
+``Simulation3DIntegral`` is duck-typed: a real ``discretize.TensorMesh`` or
+``discretize.TreeMesh`` works as well.  Conventions follow
+``BasePFSimulation.__init__`` (base.py:120-141): nodes are F-ordered (x fastest)
+and the 8 vertices of a cell are listed x-fastest, then y, then z.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _unpack_h(h):
+    """Accept discretize's ``[(dh, n)]`` / ``[(dh, n, factor)]`` notation or an array."""
+    if isinstance(h, (list, tuple)) and len(h) and isinstance(h[0], (list, tuple)):
+        out = []
+        for item in h:
+            if len(item) == 2:
+                dh, n = item
+                out.append(np.full(int(n), float(dh)))
+            else:
+                dh, n, f = item
+                n = int(n)
+                w = float(dh) * np.abs(float(f)) ** (np.arange(n) + 1)
+                out.append(w[::-1] if f < 0 else w)
+        return np.concatenate(out)
+    return np.asarray(h, dtype=np.float64).ravel()
+
+
+class TensorMesh:
+    """3-D tensor mesh.  ``origin`` is a 3-vector or a discretize-style string
+    of 'C' (centred), 'N' (negative: top/right edge at 0) or '0' per axis."""
+
+    _meshType = "TENSOR"
+
+    def __init__(self, h, origin=None):
+        if len(h) != 3:
+            raise ValueError("only 3-D tensor meshes are supported")
+        self.h = [_unpack_h(hi) for hi in h]
+        if origin is None:
+            origin = np.zeros(3)
+        if isinstance(origin, str):
+            o = []
+            for ch, hi in zip(origin, self.h):
+                o.append({"0": 0.0, "C": -hi.sum() / 2.0, "N": -hi.sum()}[ch])
+            origin = o
+        self.origin = np.asarray(origin, dtype=np.float64)
+        self.dim = 3
+
+    @property
+    def shape_cells(self):
+        return tuple(len(hi) for hi in self.h)
+
+    @property
+    def shape_nodes(self):
+        return tuple(len(hi) + 1 for hi in self.h)
+
+    @property
+    def n_cells(self):
+        return int(np.prod(self.shape_cells))
+
+    nC = n_cells
+
+    @property
+    def n_nodes(self):
+        return int(np.prod(self.shape_nodes))
+
+    @property
+    def nodes_x(self):
+        return self.origin[0] + np.r_[0.0, np.cumsum(self.h[0])]
+
+    @property
+    def nodes_y(self):
+        return self.origin[1] + np.r_[0.0, np.cumsum(self.h[1])]
+
+    @property
+    def nodes_z(self):
+        return self.origin[2] + np.r_[0.0, np.cumsum(self.h[2])]
+
+    @staticmethod
+    def _grid(x, y, z):
+        X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+        return np.c_[X.reshape(-1, order="F"), Y.reshape(-1, order="F"), Z.reshape(-1, order="F")]
+
+    @property
+    def nodes(self):
+        if getattr(self, "_nodes", None) is None:
+            self._nodes = self._grid(self.nodes_x, self.nodes_y, self.nodes_z)
+        return self._nodes
+
+    @property
+    def cell_centers(self):
+        if getattr(self, "_cc", None) is None:
+            mid = lambda v: 0.5 * (v[:-1] + v[1:])  # noqa: E731
+            self._cc = self._grid(mid(self.nodes_x), mid(self.nodes_y), mid(self.nodes_z))
+        return self._cc
+
+    @property
+    def cell_volumes(self):
+        hx, hy, hz = self.h
+        return (hx[:, None, None] * hy[None, :, None] * hz[None, None, :]).reshape(-1, order="F")
+
+    @property
+    def cell_nodes(self):
+        """(n_cells, 8) node indices, vertex order of base.py:131-140."""
+        if getattr(self, "_cell_nodes", None) is None:
+            inds = np.arange(self.n_nodes).reshape(self.shape_nodes, order="F")
+            self._cell_nodes = np.stack([
+                inds[:-1, :-1, :-1].reshape(-1, order="F"),
+                inds[1:, :-1, :-1].reshape(-1, order="F"),
+                inds[:-1, 1:, :-1].reshape(-1, order="F"),
+                inds[1:, 1:, :-1].reshape(-1, order="F"),
+                inds[:-1, :-1, 1:].reshape(-1, order="F"),
+                inds[1:, :-1, 1:].reshape(-1, order="F"),
+                inds[:-1, 1:, 1:].reshape(-1, order="F"),
+                inds[1:, 1:, 1:].reshape(-1, order="F"),
+            ], axis=-1)
+        return self._cell_nodes
+
+
+class TreeMesh:
+    """
+    Synthetic octree-style mesh: a list of axis-aligned cubic cells of
+    different levels given by their lower corner and width.  ``total_nodes``
+    holds every distinct cell vertex (hanging nodes included), and
+    ``cell_nodes`` indexes into it -- the two attributes
+    ``_get_active_nodes`` reads from a ``discretize.TreeMesh`` (base.py:377-387).
+    """
+
+    _meshType = "TREE"
+
+    def __init__(self, corners, widths):
+        corners = np.asarray(corners, dtype=np.float64).reshape(-1, 3)
+        widths = np.asarray(widths, dtype=np.float64)
+        if widths.ndim == 1:
+            widths = np.repeat(widths[:, None], 3, axis=1)
+        self.dim = 3
+        self._corners = corners
+        self._widths = widths
+        offs = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0],
+                         [0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1]], dtype=np.float64)
+        verts = corners[:, None, :] + offs[None, :, :] * widths[:, None, :]   # (nC, 8, 3)
+        flat = verts.reshape(-1, 3)
+        # exact-coordinate dedup (vertices are sums of dyadic multiples of the base width)
+        uniq, inv = np.unique(flat, axis=0, return_inverse=True)
+        self.total_nodes = np.ascontiguousarray(uniq)
+        self.cell_nodes = np.ascontiguousarray(inv.reshape(-1, 8).astype(np.int64))
+        self.cell_centers = corners + 0.5 * widths
+
+    @property
+    def n_cells(self):
+        return self._corners.shape[0]
+
+    nC = n_cells
+
+    @property
+    def nodes(self):
+        return self.total_nodes
+
+    @property
+    def cell_volumes(self):
+        return np.prod(self._widths, axis=1)
+
+
+def synthetic_octree(n_base, h, levels=3, topo=None, origin=None, refine_depth=None):
+    """
+    Octree below topography for benchmarks (BASELINE.json config 5 style).
+
+    A base grid of ``n_base`` = (nx, ny, nz) cells of width ``4h`` (for 3 levels)
+    is refined towards the surface: cells whose top is within ``refine_depth[l]``
+    of the topography are split down to level ``l``.  Cells entirely above
+    ``topo(x, y)`` are dropped (inactive).  Returns a :class:`TreeMesh` whose
+    cells are sorted in Morton-like (coarse-block) order.
+    """
+    nx, ny, nz = n_base
+    H = h * 2 ** (levels - 1)
+    if origin is None:
+        origin = np.array([-nx * H / 2.0, -ny * H / 2.0, -nz * H])
+    if topo is None:
+        topo = lambda x, y: np.zeros_like(x)  # noqa: E731
+    if refine_depth is None:
+        refine_depth = [np.inf] + [H * (levels - l) for l in range(1, levels)]
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    corners = origin + H * np.c_[ix.ravel(order="F"), iy.ravel(order="F"), iz.ravel(order="F")]
+    widths = np.full(corners.shape[0], H)
+    out_c, out_w = [], []
+    for level in range(1, levels):
+        cx = corners[:, 0] + 0.5 * widths
+        cy = corners[:, 1] + 0.5 * widths
+        top = corners[:, 2] + widths
+        depth = topo(cx, cy) - top
+        split = depth < refine_depth[level]
+        out_c.append(corners[~split])
+        out_w.append(widths[~split])
+        c, w = corners[split], widths[split] / 2.0
+        offs = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0],
+                         [0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1]], dtype=np.float64)
+        corners = (c[:, None, :] + offs[None, :, :] * w[:, None, None]).reshape(-1, 3)
+        widths = np.repeat(w, 8)
+    out_c.append(corners)
+    out_w.append(widths)
+    corners = np.concatenate(out_c)
+    widths = np.concatenate(out_w)
+    # active = centre below topography
+    cc = corners + 0.5 * widths[:, None]
+    keep = cc[:, 2] < topo(cc[:, 0], cc[:, 1])
+    corners, widths = corners[keep], widths[keep]
+    # coarse-block ordering
+    blk = np.floor((corners - origin) / H).astype(np.int64)
+    key = blk[:, 0] + nx * (blk[:, 1] + ny * blk[:, 2])
+    order = np.lexsort((corners[:, 0], corners[:, 1], corners[:, 2], key))
+    return TreeMesh(corners[order], widths[order])

@@ -1,0 +1,362 @@
+"""
+``BasePFSimulation`` with ``engine="cuda"`` -- the host-side mirror of
+simpeg/potential_fields/base.py:24-408 for the integral-equation hot path.
+
+Kept from the reference: constructor keywords, ``store_sensitivities``
+('ram' / 'forward_only'; 'disk' is rejected for this engine),
+``sensitivity_dtype`` (forced to float64 when ``forward_only``,
+base.py:196-215), ``engine`` validation with the reference's error text
+(base.py:241-256), ``_get_active_nodes`` (base.py:371-399, cached here) and
+``_get_components_and_receivers`` (base.py:401-408).
+
+New: everything below the four private methods runs on the GPU through
+``simpeg_b200.engine.CudaEngine`` (C ABI ``include/pf_cuda.h``).  Receivers are
+sharded over the ranks of ``torch.distributed`` when it is initialised
+(``simpeg_b200/sharding.py``).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.sparse.linalg import LinearOperator
+
+from ..utils import validate_active_indices, validate_string
+
+ENGINES = ("geoana", "choclo", "cuda")
+
+
+class _Zero:
+    """Stand-in for ``simpeg.utils.Zero`` (derivative of a fixed property)."""
+
+    def __matmul__(self, other):
+        return 0
+
+    __rmatmul__ = __matmul__
+
+    @property
+    def T(self):
+        return self
+
+
+class DeviceLinearOperator(LinearOperator):
+    """
+    ``scipy.sparse.linalg.LinearOperator`` whose matvec / rmatvec run on the
+    GPU.  Returned for ``G`` by ``engine="cuda"``: with ``store_sensitivities=
+    "ram"`` the products stream the device-resident ``G`` (which cannot come
+    back to the host at production sizes), with ``"forward_only"`` they
+    evaluate the kernels on the fly -- the same object the reference builds at
+    gravity/simulation.py:673-688.  ``to_numpy()`` copies a stored ``G`` to the
+    host for small problems.
+    """
+
+    def __init__(self, shape, matvec, rmatvec, to_numpy=None):
+        self._mv, self._rmv, self._to_numpy = matvec, rmatvec, to_numpy
+        super().__init__(dtype=np.float64, shape=shape)
+
+    def _matvec(self, x):
+        return self._mv(np.asarray(x, dtype=np.float64).reshape(-1))
+
+    def _rmatvec(self, x):
+        return self._rmv(np.asarray(x, dtype=np.float64).reshape(-1))
+
+    def to_numpy(self):
+        if self._to_numpy is None:
+            raise NotImplementedError(
+                "G is never stored with store_sensitivities='forward_only'")
+        return self._to_numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a if dtype is None else a.astype(dtype)
+
+
+class BasePFSimulation:
+    _physics = None            # "gravity" | "magnetics"
+    _prop_name = None          # "rho" | "chi"
+
+    def __init__(self, mesh, active_cells=None, store_sensitivities="ram", n_processes=1,
+                 sensitivity_dtype=np.float32, engine="cuda", numba_parallel=True,
+                 survey=None, sensitivity_path="./sensitivities", comm=None, device=None,
+                 **kwargs):
+        if kwargs.pop("ind_active", None) is not None:
+            raise TypeError("'ind_active' has been removed in SimPEG v0.24.0, "
+                            "please use 'active_cells' instead.")
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        self.mesh = mesh
+        self.store_sensitivities = store_sensitivities
+        self.sensitivity_dtype = sensitivity_dtype
+        self.engine = engine
+        self.numba_parallel = bool(numba_parallel)  # accepted for API parity; unused by "cuda"
+        self.survey = survey
+        self.sensitivity_path = sensitivity_path
+        self.n_processes = n_processes
+        if self.store_sensitivities == "disk":
+            raise NotImplementedError(
+                "store_sensitivities='disk' is not available with engine='cuda' "
+                "(use 'ram' or 'forward_only').")
+        n_cells = mesh.n_cells
+        if active_cells is None:
+            active_cells = np.ones(n_cells, dtype=bool)
+        else:
+            active_cells = validate_active_indices("active_cells", active_cells, n_cells)
+        self._active_cells = active_cells
+        self.nC = int(active_cells.sum())
+        self._comm = comm
+        self._device = device
+        self._model = None
+        self._engine_obj = None
+        self._active_nodes_cache = None
+
+    # ------------------------------------------------------------ properties
+    @property
+    def mesh(self):
+        return self._mesh
+
+    @mesh.setter
+    def mesh(self, value):
+        for attr in ("dim", "n_cells", "cell_nodes"):
+            if not hasattr(value, attr):
+                raise TypeError(f"mesh must be a 3D tensor or tree mesh (missing {attr!r})")
+        if value.dim != 3:
+            raise ValueError(
+                f"{type(self).__name__} mesh must be 3D, received a {value.dim}D mesh.")
+        self._mesh = value
+
+    @property
+    def active_cells(self):
+        return self._active_cells
+
+    @property
+    def store_sensitivities(self):
+        return self._store_sensitivities
+
+    @store_sensitivities.setter
+    def store_sensitivities(self, value):
+        self._store_sensitivities = validate_string(
+            "store_sensitivities", value, ["disk", "ram", "forward_only"])
+
+    @property
+    def sensitivity_dtype(self):
+        if self.store_sensitivities == "forward_only":
+            return np.float64
+        return self._sensitivity_dtype
+
+    @sensitivity_dtype.setter
+    def sensitivity_dtype(self, value):
+        if value is not np.float32 and value is not np.float64:
+            raise TypeError("sensitivity_dtype must be either np.float32 or np.float64.")
+        self._sensitivity_dtype = value
+
+    @property
+    def engine(self):
+        return self._engine
+
+    @engine.setter
+    def engine(self, value):
+        validate_string("engine", value, string_list=ENGINES, case_sensitive=True)
+        if value != "cuda":
+            raise NotImplementedError(
+                f"engine={value!r} is the reference's CPU path; this package only "
+                "provides engine='cuda'.")
+        self._engine = value
+
+    @property
+    def n_processes(self):
+        return self._n_processes
+
+    @n_processes.setter
+    def n_processes(self, value):
+        if value is not None:
+            if int(value) != value or value < 1:
+                raise ValueError("'n_processes' must be an integer >= 1")
+        self._n_processes = value
+
+    # ---------------------------------------------------- model plumbing (props)
+    @property
+    def model(self):
+        return self._model
+
+    @model.setter
+    def model(self, value):
+        if value is not None:
+            value = np.asarray(value, dtype=np.float64).reshape(-1)
+        prev = self._model
+        if value is not None and prev is not None and prev.shape == value.shape \
+                and np.array_equal(prev, value):
+            return
+        self._model = value
+        for name in self._delete_on_model_update:
+            if hasattr(self, name):
+                delattr(self, name)
+
+    @property
+    def _delete_on_model_update(self):
+        return []
+
+    def _physical_property(self, fixed, mapping):
+        if mapping is not None:
+            if self._model is None:
+                raise AttributeError(f"no model set: cannot evaluate {self._prop_name}Map * model")
+            return np.asarray(mapping * self._model, dtype=np.float64)
+        return fixed
+
+    def _property_deriv(self, mapping):
+        if mapping is None or self._model is None:
+            return _Zero()
+        d = mapping.deriv(self._model)
+        return d if sp.issparse(d) else sp.csr_matrix(d)
+
+    # ------------------------------------------------------------ mesh -> arrays
+    def _get_active_nodes(self):
+        """
+        base.py:371-399: nodes of the active cells and the (nC, 8) table of
+        indices into them.  Cached (the reference recomputes it per call).
+        """
+        if self._active_nodes_cache is not None:
+            return self._active_nodes_cache
+        mesh = self.mesh
+        if hasattr(mesh, "total_nodes"):
+            nodes = mesh.total_nodes          # TreeMesh: hanging nodes included
+        elif hasattr(mesh, "nodes"):
+            nodes = mesh.nodes
+        else:
+            raise TypeError(f"Invalid mesh of type {mesh.__class__.__name__}.")
+        cell_nodes = np.asarray(mesh.cell_nodes)
+        if self.nC != mesh.n_cells:
+            cell_nodes = cell_nodes[self.active_cells]
+            unique_nodes, active_cell_nodes = np.unique(cell_nodes, return_inverse=True)
+            nodes = np.asarray(nodes)[unique_nodes]
+            cell_nodes = active_cell_nodes.reshape(cell_nodes.shape)
+        self._active_nodes_cache = (np.asarray(nodes, dtype=np.float64), cell_nodes)
+        return self._active_nodes_cache
+
+    def _get_components_and_receivers(self):
+        """base.py:401-408"""
+        if not hasattr(self.survey, "source_field"):
+            raise AttributeError(f"The survey '{self.survey}' has no 'source_field' attribute.")
+        for receiver_object in self.survey.source_field.receiver_list:
+            yield receiver_object.components, receiver_object.locations
+
+    # ------------------------------------------------------------ device engine
+    def _n_columns(self):
+        return self.nC
+
+    def _engine_kwargs(self):
+        return {}
+
+    @property
+    def _dev(self):
+        """Lazily created CudaEngine + sharding for this simulation."""
+        if self._engine_obj is None:
+            from ..engine import CudaEngine
+            from ..sharding import Collectives, ReceiverSharding
+
+            coll = self._comm if self._comm is not None else Collectives()
+            receiver_list = [(np.asarray(loc, dtype=np.float64), list(comps))
+                             for comps, loc in self._get_components_and_receivers()]
+            self._sharding = ReceiverSharding(receiver_list, coll.rank, coll.world_size)
+            self._coll = coll
+            nodes, cell_nodes = self._get_active_nodes()
+            self._engine_obj = CudaEngine(
+                self._physics, nodes, cell_nodes, self._sharding.local_receiver_list,
+                sensitivity_dtype=self.sensitivity_dtype, device=self._device,
+                **self._engine_kwargs())
+            self._local_rows_t = self._engine_obj.torch.from_numpy(
+                self._sharding.local_rows).to(self._engine_obj.device)
+        return self._engine_obj
+
+    # local <-> global vectors -------------------------------------------------
+    def _rows_to_host(self, local_t):
+        """local rows (device) -> full (nD,) numpy vector (all-gather over ranks)."""
+        self._dev
+        full = self._coll.all_gather_rows(local_t, self._sharding)
+        return full.cpu().numpy()
+
+    def _cols_to_host(self, partial_t):
+        """partial (nP,) device vector -> numpy (all-reduce over ranks)."""
+        self._dev
+        return self._coll.all_reduce_sum(partial_t).cpu().numpy()
+
+    def _local_rows_of(self, vector):
+        """full (nD,) host vector -> local rows on the device."""
+        dev = self._dev
+        v = dev.to_device(vector, n=self._sharding.nD)
+        if self._coll.world_size == 1:
+            return v
+        return v[self._local_rows_t].contiguous()
+
+    # the four private methods of the reference, on the GPU -------------------------
+    def _forward(self, model):
+        """G @ model without storing G (gravity/simulation.py:541-583, mag 829-929)."""
+        dev = self._dev
+        fields = dev.forward_dev(dev.to_device(model, n=self._n_columns()))
+        return self._rows_to_host(fields)
+
+    def _sensitivity_matrix(self):
+        """Build the local block of G on the device (gravity/simulation.py:585-629)."""
+        return self._dev.build_G()
+
+    def _sensitivity_matrix_transpose_dot_vec(self, vector):
+        """G.T @ v without storing G (gravity/simulation.py:631-671)."""
+        dev = self._dev
+        return self._cols_to_host(dev.gt_dot_v_dev(self._local_rows_of(vector)))
+
+    def _gtg_diagonal_without_building_g(self, weights):
+        """diag(G.T W.T W G) without storing G (gravity/simulation.py:690-724)."""
+        dev = self._dev
+        return self._cols_to_host(dev.gtg_diag_dev(self._local_rows_of(weights)))
+
+    # stored-G products ---------------------------------------------------------------
+    def _G_matvec(self, x):
+        dev = self._dev
+        return self._rows_to_host(dev.gemv_dev(dev.to_device(x, n=self._n_columns())))
+
+    def _G_rmatvec(self, y):
+        dev = self._dev
+        return self._cols_to_host(dev.gemv_t_dev(self._local_rows_of(y)))
+
+    def _G_to_numpy(self):
+        if self._coll.world_size != 1:
+            raise NotImplementedError("G.to_numpy() is only available on a single process")
+        return self._dev.G_to_numpy()
+
+    def _sensitivity_matrix_as_operator(self):
+        """gravity/simulation.py:673-688"""
+        shape = (self.survey.nD, self._n_columns())
+        return DeviceLinearOperator(shape, self._forward,
+                                    self._sensitivity_matrix_transpose_dot_vec)
+
+    @property
+    def G(self):
+        """
+        Forward operator.  ``engine="cuda"`` always returns a
+        :class:`DeviceLinearOperator`; for 'ram' the matrix lives in HBM and is
+        built on first access (gravity/simulation.py:421-443).
+        """
+        if not hasattr(self, "_G"):
+            if self.store_sensitivities == "forward_only":
+                self._G = self._sensitivity_matrix_as_operator()
+            else:
+                self._sensitivity_matrix()
+                shape = (self.survey.nD, self._n_columns())
+                self._G = DeviceLinearOperator(shape, self._G_matvec, self._G_rmatvec,
+                                               self._G_to_numpy)
+        return self._G
+
+    def _warn_n_processes(self, kwargs, what):
+        if "n_processes" in kwargs:
+            warnings.warn(
+                f"The 'n_processes' will be ignored when selecting 'cuda' as the "
+                f"engine in the {what} simulation.", UserWarning, stacklevel=3)
+            self.n_processes = None
+
+    # LinearSimulation.dpred (simulation.py:698-704)
+    def dpred(self, m=None, f=None):
+        if m is None:
+            m = self.model
+        if f is not None:
+            return f
+        return self.fields(m)

@@ -1,0 +1,98 @@
+"""
+``gravity.Simulation3DIntegral`` with ``engine="cuda"`` -- mirror of
+simpeg/potential_fields/gravity/simulation.py:114-724.
+
+Public API kept: constructor keywords, ``fields/dpred/getJ/Jvec/Jtvec/
+getJtJdiag`` and the ``G`` property, data ordering (location-major,
+component-minor) and units (mGal for gx/gy/gz, Eotvos for the gradient
+components with densities in g/cc).  Model mappings stay on the host.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+from scipy.sparse.linalg import LinearOperator, aslinearoperator
+
+from ...utils import mkvc, sdiag
+from ..base import BasePFSimulation
+
+
+class Simulation3DIntegral(BasePFSimulation):
+    _physics = "gravity"
+    _prop_name = "rho"
+
+    def __init__(self, mesh, rho=None, rhoMap=None, engine="cuda", numba_parallel=True, **kwargs):
+        super().__init__(mesh, engine=engine, numba_parallel=numba_parallel,
+                         **{k: v for k, v in kwargs.items()})
+        self._rho = rho
+        self.rhoMap = rhoMap
+        self.modelMap = self.rhoMap
+        # gravity/simulation.py:186-194 (n_processes is meaningless here as well)
+        self._warn_n_processes(kwargs, "gravity")
+
+    # props.Invertible("Density") ------------------------------------------------
+    @property
+    def rho(self):
+        return self._physical_property(self._rho, self.rhoMap)
+
+    @rho.setter
+    def rho(self, value):
+        self._rho = None if value is None else np.asarray(value, dtype=np.float64)
+
+    @property
+    def rhoDeriv(self):
+        return self._property_deriv(self.rhoMap)
+
+    # API -------------------------------------------------------------------------
+    def fields(self, m):
+        """gravity/simulation.py:196-221"""
+        self.model = m
+        if self.store_sensitivities == "forward_only":
+            fields = self._forward(self.rho)
+        else:
+            fields = self.G @ self.rho
+        return np.asarray(fields)
+
+    def getJtJdiag(self, m, W=None, f=None):
+        """gravity/simulation.py:223-283 (sha256-keyed cache of diag(G.T W.T W G))."""
+        self.model = m
+        weights = (W.diagonal() ** 2 if W is not None
+                   else np.ones(self.survey.nD, dtype=np.float64))
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        weights_sha256 = hashlib.sha256(weights)
+        use_cached = (hasattr(self, "_gtg_diagonal") and hasattr(self, "_weights_sha256")
+                      and self._weights_sha256.digest() == weights_sha256.digest())
+        if not use_cached:
+            self._gtg_diagonal = self._get_gtg_diagonal(weights)
+            self._weights_sha256 = weights_sha256
+        diagonal = mkvc((sdiag(np.sqrt(self._gtg_diagonal)) @ self.rhoDeriv).power(2).sum(axis=0))
+        return diagonal
+
+    def _get_gtg_diagonal(self, weights):
+        """gravity/simulation.py:285-316"""
+        if self.store_sensitivities == "forward_only":
+            return self._gtg_diagonal_without_building_g(weights)
+        dev = self._dev
+        self.G  # make sure the matrix exists
+        return self._cols_to_host(dev.colsumsq_dev(self._local_rows_of(weights)))
+
+    def getJ(self, m, f=None):
+        """gravity/simulation.py:318-355: always a LinearOperator for engine='cuda'."""
+        self.model = m
+        return self.G @ aslinearoperator(self.rhoDeriv)
+
+    def Jvec(self, m, v, f=None):
+        """gravity/simulation.py:357-387"""
+        self.model = m
+        dmu_dm_v = self.rhoDeriv @ v
+        return np.asarray(self.G @ np.asarray(dmu_dm_v, dtype=np.float64))
+
+    def Jtvec(self, m, v, f=None):
+        """gravity/simulation.py:389-419"""
+        self.model = m
+        Jtvec = self.G.T @ np.asarray(v, dtype=np.float64)
+        return np.asarray(self.rhoDeriv.T @ Jtvec)
+
+
+__all__ = ["Simulation3DIntegral", "LinearOperator"]

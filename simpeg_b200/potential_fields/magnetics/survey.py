@@ -1,0 +1,6 @@
+"""magnetics/survey.py mirror."""
+from .._survey import BaseSurvey
+
+
+class Survey(BaseSurvey):
+    pass

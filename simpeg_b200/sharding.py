@@ -1,0 +1,126 @@
+"""
+Receiver-row sharding of G across processes (one process per GPU).
+
+Every row of G depends on one receiver only -- the reference parallelises the
+same axis with ``prange`` over receivers (gravity/_numba/_3d_mesh.py:145) -- so
+each rank owns a contiguous block of the locations of every receiver object
+and therefore the rows
+
+    row = object_offset + i_location * n_components + i_component
+
+of those locations.  The mesh and the model vectors are replicated.  Only two
+exchanges exist on the path:
+
+* ``dpred`` / ``Jvec`` / ``G @ m``: every rank holds the entries of its rows ->
+  all-gather into the full (nD,) vector;
+* ``Jtvec`` / ``G.T @ v`` / ``getJtJdiag``: every rank holds a partial (nP,)
+  vector -> all-reduce (sum).
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is the transport.
+Building G needs no communication at all.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def block_bounds(n: int, world_size: int, rank: int):
+    """Contiguous block [lo, hi) of ``n`` items for ``rank`` (sizes differ by <= 1)."""
+    base, rem = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+class ReceiverSharding:
+    """
+    Parameters
+    ----------
+    receiver_list : list of (locations (R, 3), components list[str]) -- the whole survey
+    rank, world_size : position of this process
+    """
+
+    def __init__(self, receiver_list, rank=0, world_size=1):
+        if not (0 <= rank < world_size):
+            raise ValueError(f"rank {rank} outside world of size {world_size}")
+        self.rank = int(rank)
+        self.world_size = int(world_size)
+        self._objects = []
+        offset = 0
+        for locations, components in receiver_list:
+            components = [components] if isinstance(components, str) else list(components)
+            locations = np.asarray(locations, dtype=np.float64).reshape(-1, 3)
+            self._objects.append((locations, components, offset))
+            offset += locations.shape[0] * len(components)
+        self.nD = offset
+        self.local_receiver_list = []
+        for locations, components, _ in self._objects:
+            lo, hi = block_bounds(locations.shape[0], world_size, rank)
+            self.local_receiver_list.append((np.ascontiguousarray(locations[lo:hi]), components))
+        self.local_rows = self.rows_of_rank(self.rank)
+
+    def rows_of_rank(self, rank):
+        """Global row index of every local row of ``rank``, in local row order."""
+        rows = []
+        for locations, components, offset in self._objects:
+            lo, hi = block_bounds(locations.shape[0], self.world_size, rank)
+            c = len(components)
+            rows.append(offset + np.arange(lo * c, hi * c, dtype=np.int64))
+        return np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+
+    @property
+    def n_local_rows(self):
+        return int(self.local_rows.size)
+
+    def max_local_rows(self):
+        return max(self.rows_of_rank(r).size for r in range(self.world_size))
+
+
+class Collectives:
+    """Thin wrapper over ``torch.distributed`` (a no-op for a single process)."""
+
+    def __init__(self, group=None, world_size=None, rank=None):
+        self.group = group
+        self._dist = None
+        if world_size is None:
+            try:
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized():
+                    self._dist = dist
+                    world_size = dist.get_world_size(group)
+                    rank = dist.get_rank(group)
+            except ImportError:  # pragma: no cover
+                pass
+        elif world_size > 1:
+            import torch.distributed as dist
+
+            self._dist = dist
+        self.world_size = 1 if world_size is None else int(world_size)
+        self.rank = 0 if rank is None else int(rank)
+        if self.world_size == 1:
+            self._dist = None
+
+    def all_reduce_sum(self, tensor):
+        """In-place sum over ranks of a partial (nP,) vector (Jtvec, JtJ diagonal)."""
+        if self._dist is not None:
+            self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
+        return tensor
+
+    def all_gather_rows(self, local, sharding: ReceiverSharding):
+        """Assemble the full (nD,) vector from every rank's local rows (dpred, Jvec)."""
+        import torch
+
+        full = torch.zeros(sharding.nD, dtype=local.dtype, device=local.device)
+        if self._dist is None:
+            full[torch.from_numpy(sharding.local_rows).to(local.device)] = local
+            return full
+        m = sharding.max_local_rows()
+        padded = torch.zeros(m, dtype=local.dtype, device=local.device)
+        padded[: local.numel()] = local
+        gathered = torch.empty(m * self.world_size, dtype=local.dtype, device=local.device)
+        self._dist.all_gather_into_tensor(gathered, padded, group=self.group)
+        for r in range(self.world_size):
+            rows = sharding.rows_of_rank(r)
+            full[torch.from_numpy(rows).to(local.device)] = gathered[r * m: r * m + rows.size]
+        return full

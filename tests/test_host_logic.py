@@ -1,0 +1,185 @@
+"""CPU: host-side mirror of the reference interface -- validation, errors,
+ordering, mappings, sharding arithmetic (no GPU, no kernels)."""
+import numpy as np
+import pytest
+
+from sim_fixtures import gravity_survey, magnetic_survey, small_mesh
+from simpeg_b200 import maps
+from simpeg_b200.meshes import TensorMesh
+from simpeg_b200.potential_fields import gravity, magnetics
+from simpeg_b200.sharding import ReceiverSharding, block_bounds
+from simpeg_b200.utils import dip_azimuth2cartesian
+
+
+def test_invalid_engine_message():
+    # pinned by tests/pf/test_forward_Grav_Linear.py:334-339 (tuple extended by 'cuda')
+    msg = r"'engine' must be in \('geoana', 'choclo', 'cuda'\). Got 'invalid engine'"
+    with pytest.raises(ValueError, match=msg):
+        gravity.Simulation3DIntegral(small_mesh(), engine="invalid engine")
+
+
+def test_cpu_engines_are_not_provided():
+    with pytest.raises(NotImplementedError, match="only provides engine='cuda'"):
+        gravity.Simulation3DIntegral(small_mesh(), engine="choclo")
+
+
+@pytest.mark.parametrize("bad", [np.float16, float, "float64", np.dtype("float64")])
+def test_invalid_sensitivity_dtype(bad):
+    # base.py:211-214; tests/pf/test_forward_Grav_Linear.py:321-332
+    sim = gravity.Simulation3DIntegral(small_mesh())
+    with pytest.raises(TypeError, match="sensitivity_dtype must be either np.float32 or np.float64."):
+        sim.sensitivity_dtype = bad
+
+
+def test_sensitivity_dtype_defaults():
+    # base.py:86 default float32; forced float64 when forward_only (205-206)
+    assert gravity.Simulation3DIntegral(small_mesh()).sensitivity_dtype is np.float32
+    sim = gravity.Simulation3DIntegral(small_mesh(), store_sensitivities="forward_only",
+                                       sensitivity_dtype=np.float32)
+    assert sim.sensitivity_dtype is np.float64
+
+
+def test_disk_not_available_and_bad_store():
+    with pytest.raises(NotImplementedError, match="disk"):
+        gravity.Simulation3DIntegral(small_mesh(), store_sensitivities="disk")
+    with pytest.raises(ValueError, match="store_sensitivities"):
+        gravity.Simulation3DIntegral(small_mesh(), store_sensitivities="tape")
+
+
+def test_n_processes_warning():
+    # tests/pf/test_forward_Grav_Linear.py:341-349
+    with pytest.warns(UserWarning, match="The 'n_processes' will be ignored when selecting 'cuda'"):
+        sim = gravity.Simulation3DIntegral(small_mesh(), n_processes=2)
+    assert sim.n_processes is None
+
+
+def test_mesh_must_be_3d():
+    class Mesh2D:
+        dim, n_cells, cell_nodes = 2, 4, None
+
+    with pytest.raises(ValueError, match="mesh must be 3D, received a 2D mesh"):
+        gravity.Simulation3DIntegral(Mesh2D())
+    with pytest.raises(TypeError):
+        gravity.Simulation3DIntegral(object())
+
+
+def test_ind_active_removed():
+    with pytest.raises(TypeError, match="'ind_active' has been removed"):
+        gravity.Simulation3DIntegral(small_mesh(), ind_active=np.ones(64, dtype=bool))
+
+
+def test_invalid_components():
+    with pytest.raises(ValueError, match="'component' must be in"):
+        gravity.receivers.Point(np.zeros((1, 3)), components="tmi")
+    with pytest.raises(ValueError, match="'component' must be in"):
+        magnetics.receivers.Point(np.zeros((1, 3)), components="gz")
+
+
+def test_model_type_and_amplitude_validation():
+    with pytest.raises(ValueError, match="model_type"):
+        magnetics.Simulation3DIntegral(small_mesh(), model_type="tensor")
+    sim = magnetics.Simulation3DIntegral(small_mesh(), survey=magnetic_survey(["bx", "by", "bz"]),
+                                         is_amplitude_data=True)
+    assert sim.nD == sim.survey.nD // 3
+    with pytest.raises(NotImplementedError, match="getJ"):
+        sim.getJ(np.zeros(64))
+
+
+def test_no_cuda_device_fails_loudly():
+    """engine='cuda' never falls back: without a device the first use raises."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    sim = gravity.Simulation3DIntegral(small_mesh(), survey=gravity_survey(),
+                                       rhoMap=maps.IdentityMap(nP=64))
+    with pytest.raises(RuntimeError, match="requires a CUDA device"):
+        sim.dpred(np.zeros(64))
+
+
+def test_get_active_nodes_tensor_all_active():
+    # tests/pf/test_base_pf_simulation.py:109-186
+    mesh = small_mesh()
+    sim = gravity.Simulation3DIntegral(mesh, survey=gravity_survey())
+    nodes, cell_nodes = sim._get_active_nodes()
+    assert np.array_equal(nodes, mesh.nodes)
+    assert np.array_equal(cell_nodes, mesh.cell_nodes)
+
+
+def test_get_active_nodes_with_inactive_cells():
+    mesh = small_mesh()
+    active = np.ones(mesh.n_cells, dtype=bool)
+    active[:16] = False          # bottom layer inactive
+    sim = gravity.Simulation3DIntegral(mesh, survey=gravity_survey(), active_cells=active)
+    nodes, cell_nodes = sim._get_active_nodes()
+    assert sim.nC == 48
+    assert cell_nodes.shape == (48, 8)
+    assert nodes.shape[0] == 25 * 4                     # bottom node layer dropped
+    assert np.array_equal(nodes[cell_nodes], mesh.nodes[mesh.cell_nodes[active]])
+    # integer indices are accepted too (validate_active_indices)
+    sim2 = gravity.Simulation3DIntegral(mesh, survey=gravity_survey(),
+                                        active_cells=np.nonzero(active)[0])
+    assert sim2.nC == 48
+
+
+def test_components_and_receivers_ordering():
+    # base.py:401-408; data are location-major, component-minor (tests/pf/test_pf_survey.py:32-55)
+    survey = magnetic_survey(["tmi", "bx"], two_objects=True)
+    sim = magnetics.Simulation3DIntegral(small_mesh(), survey=survey)
+    got = list(sim._get_components_and_receivers())
+    assert [c for c, _ in got] == [["tmi", "bx"], ["bz", "tmi"]]
+    assert survey.nD == 7 * 2 + 9 * 2
+    assert list(survey.vnD) == [14, 18]
+
+
+def test_b0_matches_reference_convention():
+    # magnetics/sources.py:104-109 + utils/mat_utils.py:411-424; doctest values
+    v = dip_azimuth2cartesian(30, 60)[0]
+    assert np.allclose(v, [0.75, 0.4330127, -0.5])
+    src = magnetics.sources.UniformBackgroundField([], amplitude=50000, inclination=90, declination=0)
+    assert np.allclose(src.b0, [0, 0, -50000], atol=1e-9)
+
+
+def test_maps():
+    m = np.log(np.array([1.0, 2.0, 3.0]))
+    e = maps.ExpMap(nP=3)
+    assert np.allclose(e * m, [1, 2, 3])
+    assert np.allclose(e.deriv(m).toarray(), np.diag([1.0, 2.0, 3.0]))
+    i = maps.IdentityMap(nP=3)
+    assert np.allclose((i.deriv(m) @ m), m)
+
+
+def test_tensor_mesh_matches_discretize_conventions():
+    mesh = TensorMesh([[(5.0, 4)], [(5.0, 4)], [(5.0, 4)]], "CCN")
+    assert mesh.n_cells == 64 and mesh.n_nodes == 125
+    assert mesh.nodes[0].tolist() == [-10.0, -10.0, -20.0]
+    assert mesh.nodes[-1].tolist() == [10.0, 10.0, 0.0]
+    assert mesh.nodes[1, 0] - mesh.nodes[0, 0] == 5.0          # x fastest
+    cn = mesh.cell_nodes[0]
+    assert cn.tolist() == [0, 1, 5, 6, 25, 26, 30, 31]
+    assert np.allclose(mesh.cell_centers[0], [-7.5, -7.5, -17.5])
+
+
+def test_block_bounds_cover_everything():
+    for n in (0, 1, 7, 16, 101):
+        for world in (1, 2, 3, 8):
+            spans = [block_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_receiver_sharding_rows():
+    loc_a, loc_b = np.zeros((5, 3)), np.ones((4, 3))
+    rlist = [(loc_a, ["gxx", "gz"]), (loc_b, ["gz"])]
+    all_rows = []
+    for rank in range(3):
+        sh = ReceiverSharding(rlist, rank, 3)
+        assert sh.nD == 14
+        n_local = sum(l.shape[0] * len(c) for l, c in sh.local_receiver_list)
+        assert n_local == sh.n_local_rows
+        all_rows.append(sh.local_rows)
+    assert np.array_equal(np.sort(np.concatenate(all_rows)), np.arange(14))
+    # rank 0 owns locations [0,2) of object a -> rows 0..3, and [0,2) of b -> rows 10, 11
+    assert all_rows[0].tolist() == [0, 1, 2, 3, 10, 11]

@@ -1,0 +1,75 @@
+"""CPU: the tile planner covers every active cell exactly once and reproduces
+the (nodes, cell_nodes) geometry bit-for-bit inside every tile."""
+import numpy as np
+import pytest
+
+from simpeg_b200.meshes import TensorMesh, synthetic_octree
+from simpeg_b200.tiling import TILE_CELLS, TILE_NODES, build_tile_plan
+
+
+def check_plan(nodes, cell_nodes, method="auto"):
+    plan = build_tile_plan(nodes, cell_nodes, method)
+    cols = plan.tile_cell_col
+    valid = cols >= 0
+    assert valid.sum() == cell_nodes.shape[0]
+    assert np.array_equal(np.sort(cols[valid]), np.arange(cell_nodes.shape[0]))
+    tt, ss = np.nonzero(valid)
+    local = plan.tile_cell_nodes[tt, ss]
+    assert (local < plan.tile_n_nodes[tt][:, None]).all()
+    xyz = plan.tile_xyz[tt[:, None], :, local]
+    assert np.array_equal(xyz, nodes[cell_nodes[cols[tt, ss]]])
+    assert plan.tile_n_nodes.max() <= TILE_NODES
+    assert valid.sum(axis=1).max() <= TILE_CELLS
+    # columns ascend inside a tile (contiguous G writes)
+    for t in range(min(plan.n_tiles, 8)):
+        c = cols[t][cols[t] >= 0]
+        assert np.all(np.diff(c) > 0)
+    return plan
+
+
+def test_tensor_mesh_bricks():
+    mesh = TensorMesh([np.full(40, 5.0), np.full(40, 5.0), np.full(20, 5.0)], "CCN")
+    plan = check_plan(mesh.nodes, mesh.cell_nodes)
+    assert plan.method == "brick"
+    assert plan.n_tiles == 64            # 10 x 10 x 5 bricks of 500 cells
+    assert plan.nodes_per_cell < 1.5
+
+
+def test_rcb_on_tensor_mesh():
+    mesh = TensorMesh([np.full(20, 5.0), np.full(17, 5.0), np.full(9, 5.0)], "CCN")
+    plan = check_plan(mesh.nodes, mesh.cell_nodes, "rcb")
+    assert plan.method == "rcb"
+
+
+def test_nonuniform_and_small():
+    mesh = TensorMesh([[(2.0, 3, -1.3), (2.0, 5), (2.0, 3, 1.3)], [(3.0, 4)], [(1.0, 2)]], "CCN")
+    plan = check_plan(mesh.nodes, mesh.cell_nodes)
+    assert plan.n_tiles == 1
+
+
+def test_inactive_cells_compact_nodes():
+    mesh = TensorMesh([np.full(12, 1.0)] * 3, "CCN")
+    cc = mesh.cell_centers
+    active = cc[:, 2] < -2.0 + 0.3 * cc[:, 0]
+    cn = mesh.cell_nodes[active]
+    uniq, inv = np.unique(cn, return_inverse=True)
+    check_plan(mesh.nodes[uniq], inv.reshape(cn.shape))
+
+
+def test_octree_with_hanging_nodes():
+    topo = lambda x, y: 5.0 * np.exp(-0.5 * ((x / 30.0) ** 2 + (y / 30.0) ** 2))  # noqa: E731
+    mesh = synthetic_octree((6, 6, 4), 2.5, levels=3, topo=topo)
+    assert mesh.n_cells > 2000
+    widths = np.unique(np.round(mesh.cell_volumes ** (1 / 3), 6))
+    assert len(widths) == 3              # three refinement levels present
+    check_plan(mesh.total_nodes, mesh.cell_nodes)
+    check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb")
+
+
+def test_empty_and_invalid():
+    plan = build_tile_plan(np.zeros((0, 3)), np.zeros((0, 8), dtype=np.int64))
+    assert plan.n_tiles == 0
+    with pytest.raises(ValueError):
+        build_tile_plan(np.zeros((4, 2)), np.zeros((1, 8), dtype=np.int64))
+    with pytest.raises(ValueError):
+        build_tile_plan(np.zeros((4, 3)), np.full((1, 8), 7, dtype=np.int64))
