@@ -141,8 +141,10 @@ class Simulation3DIntegral(BasePFSimulation):
     def getJtJdiag(self, m, W=None, f=None):
         """magnetics/simulation.py:346-406"""
         self.model = m
+        # one weight per datum: per row, or per location for amplitude data (the
+        # reference's default of survey.nD ones overruns its own loop at 446 then)
         weights = (W.diagonal() ** 2 if W is not None
-                   else np.ones(self.survey.nD, dtype=np.float64))
+                   else np.ones(self.nD, dtype=np.float64))
         weights = np.ascontiguousarray(weights, dtype=np.float64)
         weights_sha256 = hashlib.sha256(weights)
         use_cached = (hasattr(self, "_gtg_diagonal") and hasattr(self, "_weights_sha256")

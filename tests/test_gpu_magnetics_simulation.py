@@ -131,10 +131,12 @@ def test_amplitude_data(model_type):
     weights = rng.uniform(0.5, 1.5, size=sim.nD)
     rows = amp_deriv[0][:, None] * G[::3] + amp_deriv[1][:, None] * G[1::3] + amp_deriv[2][:, None] * G[2::3]
     expected_d = np.einsum("i,ij,ij->j", weights**2, rows, rows)
-    got = sim.getJtJdiag(model, W=sp.diags(np.repeat(weights, 3)))
-    # the reference passes the (nD,) weights and indexes the first n_loc entries
-    got_ref_style = got
-    assert got_ref_style.shape == expected_d.shape
+    got = sim.getJtJdiag(model, W=sp.diags(weights))
+    assert vec_rel(got, expected_d) <= RTOL_NORMWISE
+    # cache is dropped on a model update for amplitude data (simulation.py:822-827)
+    assert hasattr(sim, "_gtg_diagonal")
+    sim.model = model * 1.1
+    assert not hasattr(sim, "_gtg_diagonal") and getattr(sim, "_ampDeriv_dev", None) is None
 
 
 def test_amplitude_forward_only_diag_not_implemented():
