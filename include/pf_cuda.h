@@ -100,6 +100,8 @@ typedef struct {
 
 int pf_abi_version(void);
 const char *pf_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far */
+int64_t pf_launch_count(void);
 
 /* number of columns of G for a job: nC (gravity, scalar) or 3 nC (vector) */
 int64_t pf_job_columns(const pf_plan *plan, const pf_job *job);

@@ -551,6 +551,7 @@ int launch_tile_kernel(const LaunchParams &p, cudaStream_t stream)
     PF_CHECK_ARG(chunks <= 65535, "too many receiver chunks");
     dim3 grid((unsigned)p.plan.n_tiles, (unsigned)chunks);
     kernel<<<grid, PF_THREADS, smem, stream>>>(p);
+    PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
 }
@@ -633,6 +634,7 @@ extern "C" int pf_forward(const pf_plan *plan, const pf_job *job, const double *
         q.fields = fields;
         const int64_t n_local = job->n_receivers * p.n_desc;
         pf_reduce_forward_kernel<<<(unsigned)pf_ceil_div(n_local, 256), 256, 0, (cudaStream_t)stream>>>(q);
+    PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;
@@ -672,6 +674,7 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
         if (st != PF_OK) return st;
         pf_reduce_columns_kernel<<<(unsigned)pf_ceil_div(nP, 256), 256, 0, (cudaStream_t)stream>>>(
             p.partial, chunks, nP, out);
+    PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -21,6 +22,8 @@ constexpr int PF_NPT = PF_TILE_NODES / PF_THREADS;
 constexpr double PF_NEWTON_G = 6.6743e-11;
 
 void pf_set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_pf_launches;
+#define PF_COUNT_LAUNCH() (g_pf_launches.fetch_add(1, std::memory_order_relaxed))
 
 #define PF_CHECK_ARG(cond, msg)                                   \
     do {                                                          \

@@ -273,9 +273,11 @@ int launch_column(const void *G, int64_t rows, int64_t cols, int64_t ld, const d
     else
         column_kernel<GT, MODE, false><<<grid, THREADS, 0, stream>>>((const GT *)G, rows, cols, ld, yv, amp,
                                                                      rows_per_split, target);
+    PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     if (used_splits > 1) {
         reduce_overwrite_kernel<<<(unsigned)pf_ceil_div(cols, 256), 256, 0, stream>>>(ws, used_splits, cols, out);
+    PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;
@@ -300,6 +302,7 @@ int fill_zero(double *p, int64_t n, cudaStream_t stream)
 {
     if (n <= 0) return PF_OK;
     fill_zero_kernel<<<(unsigned)pf_ceil_div(n, 256), 256, 0, stream>>>(p, n);
+    PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
 }
@@ -339,15 +342,18 @@ extern "C" int pf_gemv(const void *G, int64_t rows, int64_t cols, int64_t ld, in
             gemv_kernel<double, true><<<grid, THREADS, 0, stream>>>((const double *)G, rows, cols, ld, x, target);
         else
             gemv_kernel<double, false><<<grid, THREADS, 0, stream>>>((const double *)G, rows, cols, ld, x, target);
+    PF_COUNT_LAUNCH();
     } else {
         if (aligned_for_vectors<float>(G, ld))
             gemv_kernel<float, true><<<grid, THREADS, 0, stream>>>((const float *)G, rows, cols, ld, x, target);
         else
             gemv_kernel<float, false><<<grid, THREADS, 0, stream>>>((const float *)G, rows, cols, ld, x, target);
+    PF_COUNT_LAUNCH();
     }
     PF_CUDA_OK(cudaGetLastError());
     if (chunks > 1) {
         reduce_overwrite_kernel<<<(unsigned)pf_ceil_div(rows, 256), 256, 0, stream>>>(target, chunks, rows, y);
+    PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;
@@ -455,6 +461,7 @@ extern "C" int pf_amp_normalize(const double *b_xyz, int64_t n_loc, double *amp,
     PF_CHECK_ARG(b_xyz != nullptr, "null b_xyz");
     amp_normalize_kernel<<<(unsigned)pf_ceil_div(n_loc, 256), 256, 0, (cudaStream_t)stream>>>(b_xyz, n_loc, amp,
                                                                                                ampderiv);
+    PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
 }
@@ -466,6 +473,7 @@ extern "C" int pf_amp_combine(const double *ampderiv, const double *jv, int64_t 
     if (n_loc == 0) return PF_OK;
     PF_CHECK_ARG(ampderiv && jv && out, "null pointer");
     amp_combine_kernel<<<(unsigned)pf_ceil_div(n_loc, 256), 256, 0, (cudaStream_t)stream>>>(ampderiv, jv, n_loc, out);
+    PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
 }
@@ -477,6 +485,7 @@ extern "C" int pf_amp_spread(const double *ampderiv, const double *v, int64_t n_
     if (n_loc == 0) return PF_OK;
     PF_CHECK_ARG(ampderiv && v && out, "null pointer");
     amp_spread_kernel<<<(unsigned)pf_ceil_div(n_loc, 256), 256, 0, (cudaStream_t)stream>>>(ampderiv, v, n_loc, out);
+    PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
 }
@@ -514,11 +523,13 @@ extern "C" int pf_probe_fp64_peak(double *flops, void *stream_)
     PF_CUDA_OK(cudaEventCreate(&e0));
     PF_CUDA_OK(cudaEventCreate(&e1));
     const int blocks = 148 * 8 * 4;
-    dfma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, 0.999999, 1e-9);  // warm-up
+    dfma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, 0.999999, 1e-9);
+    PF_COUNT_LAUNCH();
     float best_ms = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, stream);
         dfma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, 0.999999, 1e-9);
+    PF_COUNT_LAUNCH();
         cudaEventRecord(e1, stream);
         cudaError_t err = cudaEventSynchronize(e1);
         if (err != cudaSuccess) {

@@ -112,7 +112,6 @@ class CudaEngine:
         self.G = None
         self.ld = 0
         self._ws = None
-        self.launches = 0  # kernels launched through the C ABI (bench bookkeeping)
 
     # ------------------------------------------------------------------ utils
     def _stream(self):
@@ -149,7 +148,6 @@ class CudaEngine:
             for job in self.jobs:
                 _lib.check(self.lib.pf_build_G(*self._jp(job), self.G.data_ptr(), self.ld,
                                                self._g_code, self._stream()), "pf_build_G")
-                self.launches += 1
         return self.G
 
     def forward_dev(self, model_t, out=None):
@@ -164,7 +162,6 @@ class CudaEngine:
                 _lib.check(self.lib.pf_forward(*self._jp(job), model_t.data_ptr(), fields.data_ptr(),
                                                ws.data_ptr(), ws.numel() * 8, self._stream()),
                            "pf_forward")
-                self.launches += 2
         return fields
 
     def _column_sink(self, fn, wsfn, vec_t, name, out=None):
@@ -177,7 +174,6 @@ class CudaEngine:
                 ws = self._workspace(nbytes)
                 _lib.check(fn(*self._jp(job), vec_t.data_ptr(), result.data_ptr(), ws.data_ptr(),
                               ws.numel() * 8, self._stream()), name)
-                self.launches += 2
         return result
 
     def gt_dot_v_dev(self, v_t, out=None):
@@ -205,7 +201,6 @@ class CudaEngine:
             _lib.check(self.lib.pf_gemv(G.data_ptr(), self.n_rows, self.nP, self.ld, self._g_code,
                                         x_t.data_ptr(), y.data_ptr(), ws.data_ptr(), ws.numel() * 8,
                                         self._stream()), "pf_gemv")
-            self.launches += 2
         return y
 
     def gemv_t_dev(self, y_t, out=None):
@@ -217,7 +212,6 @@ class CudaEngine:
             _lib.check(self.lib.pf_gemv_t(G.data_ptr(), self.n_rows, self.nP, self.ld, self._g_code,
                                           y_t.data_ptr(), z.data_ptr(), ws.data_ptr(), ws.numel() * 8,
                                           self._stream()), "pf_gemv_t")
-            self.launches += 2
         return z
 
     def colsumsq_dev(self, w_t, out=None):
@@ -229,7 +223,6 @@ class CudaEngine:
             _lib.check(self.lib.pf_colsumsq(G.data_ptr(), self.n_rows, self.nP, self.ld, self._g_code,
                                             w_t.data_ptr(), d.data_ptr(), ws.data_ptr(), ws.numel() * 8,
                                             self._stream()), "pf_colsumsq")
-            self.launches += 2
         return d
 
     # --------------------------------------------------------------- amplitude
@@ -242,7 +235,6 @@ class CudaEngine:
             ad = torch.empty((3, n_loc), dtype=torch.float64, device=self.device)
             _lib.check(self.lib.pf_amp_normalize(b_t.data_ptr(), n_loc, amp.data_ptr(), ad.data_ptr(),
                                                  self._stream()), "pf_amp_normalize")
-            self.launches += 1
         return amp, ad
 
     def amp_combine_dev(self, ad_t, jv_t):
@@ -252,7 +244,6 @@ class CudaEngine:
             out = torch.empty(n_loc, dtype=torch.float64, device=self.device)
             _lib.check(self.lib.pf_amp_combine(ad_t.data_ptr(), jv_t.data_ptr(), n_loc, out.data_ptr(),
                                                self._stream()), "pf_amp_combine")
-            self.launches += 1
         return out
 
     def amp_spread_dev(self, ad_t, v_t):
@@ -262,7 +253,6 @@ class CudaEngine:
             out = torch.empty(3 * n_loc, dtype=torch.float64, device=self.device)
             _lib.check(self.lib.pf_amp_spread(ad_t.data_ptr(), v_t.data_ptr(), n_loc, out.data_ptr(),
                                               self._stream()), "pf_amp_spread")
-            self.launches += 1
         return out
 
     def colsumsq_amp_dev(self, w_t, ad_t):
@@ -276,13 +266,17 @@ class CudaEngine:
                                                 w_t.data_ptr(), ad_t.data_ptr(), d.data_ptr(),
                                                 ws.data_ptr(), ws.numel() * 8, self._stream()),
                        "pf_colsumsq_amp")
-            self.launches += 2
         return d
 
     def G_to_numpy(self):
         """Copy the local block of G to the host (small problems / tests only)."""
         G = self._need_G()
         return G[:, : self.nP].cpu().numpy()
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by libpf_cuda.so in this process so far."""
+    return int(_lib.load_library().pf_launch_count())
 
 
 def probe_fp64_peak(device=None):
