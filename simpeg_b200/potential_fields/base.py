@@ -72,6 +72,61 @@ class DeviceLinearOperator(LinearOperator):
         return a if dtype is None else a.astype(dtype)
 
 
+class ShardedDeviceOps:
+    """
+    Host-vector <-> device operations of one simulation: the CUDA engine of the
+    local receiver shard plus the two exchanges of the path (all-gather of
+    rows, all-reduce of column partials).  Holds no reference to the
+    simulation object.
+    """
+
+    def __init__(self, engine, coll, sharding):
+        self.engine, self.coll, self.sharding = engine, coll, sharding
+        self._local_rows_t = engine.torch.from_numpy(sharding.local_rows).to(engine.device)
+
+    # local <-> global vectors
+    def rows_to_host(self, local_t):
+        """local rows (device) -> full (nD,) numpy vector (all-gather over ranks)."""
+        if self.coll.world_size == 1:
+            return local_t.cpu().numpy()
+        return self.coll.all_gather_rows(local_t, self.sharding).cpu().numpy()
+
+    def cols_to_host(self, partial_t):
+        """partial (nP,) device vector -> numpy (all-reduce over ranks)."""
+        return self.coll.all_reduce_sum(partial_t).cpu().numpy()
+
+    def local_rows_of(self, vector):
+        """full (nD,) host vector -> local rows on the device."""
+        v = self.engine.to_device(vector, n=self.sharding.nD)
+        if self.coll.world_size == 1:
+            return v
+        return v[self._local_rows_t].contiguous()
+
+    # matrix-free
+    def forward(self, model):
+        eng = self.engine
+        return self.rows_to_host(eng.forward_dev(eng.to_device(model, n=eng.nP)))
+
+    def gt_dot_v(self, vector):
+        return self.cols_to_host(self.engine.gt_dot_v_dev(self.local_rows_of(vector)))
+
+    def gtg_diag(self, weights):
+        return self.cols_to_host(self.engine.gtg_diag_dev(self.local_rows_of(weights)))
+
+    # stored G
+    def gemv(self, x):
+        eng = self.engine
+        return self.rows_to_host(eng.gemv_dev(eng.to_device(x, n=eng.nP)))
+
+    def gemv_t(self, y):
+        return self.cols_to_host(self.engine.gemv_t_dev(self.local_rows_of(y)))
+
+    def G_to_numpy(self):
+        if self.coll.world_size != 1:
+            raise NotImplementedError("G.to_numpy() is only available on a single process")
+        return self.engine.G_to_numpy()
+
+
 class BasePFSimulation:
     _physics = None            # "gravity" | "magnetics"
     _prop_name = None          # "rho" | "chi"
@@ -248,8 +303,8 @@ class BasePFSimulation:
         return {}
 
     @property
-    def _dev(self):
-        """Lazily created CudaEngine + sharding for this simulation."""
+    def _ops(self):
+        """Lazily created device operations (engine + sharding) of this simulation."""
         if self._engine_obj is None:
             from ..engine import CudaEngine
             from ..sharding import Collectives, ReceiverSharding
@@ -257,43 +312,40 @@ class BasePFSimulation:
             coll = self._comm if self._comm is not None else Collectives()
             receiver_list = [(np.asarray(loc, dtype=np.float64), list(comps))
                              for comps, loc in self._get_components_and_receivers()]
-            self._sharding = ReceiverSharding(receiver_list, coll.rank, coll.world_size)
-            self._coll = coll
+            sharding = ReceiverSharding(receiver_list, coll.rank, coll.world_size)
             nodes, cell_nodes = self._get_active_nodes()
-            self._engine_obj = CudaEngine(
-                self._physics, nodes, cell_nodes, self._sharding.local_receiver_list,
+            engine = CudaEngine(
+                self._physics, nodes, cell_nodes, sharding.local_receiver_list,
                 sensitivity_dtype=self.sensitivity_dtype, device=self._device,
                 **self._engine_kwargs())
-            self._local_rows_t = self._engine_obj.torch.from_numpy(
-                self._sharding.local_rows).to(self._engine_obj.device)
+            self._engine_obj = ShardedDeviceOps(engine, coll, sharding)
         return self._engine_obj
 
-    # local <-> global vectors -------------------------------------------------
+    @property
+    def _dev(self):
+        return self._ops.engine
+
+    @property
+    def _coll(self):
+        return self._ops.coll
+
+    @property
+    def _sharding(self):
+        return self._ops.sharding
+
     def _rows_to_host(self, local_t):
-        """local rows (device) -> full (nD,) numpy vector (all-gather over ranks)."""
-        self._dev
-        full = self._coll.all_gather_rows(local_t, self._sharding)
-        return full.cpu().numpy()
+        return self._ops.rows_to_host(local_t)
 
     def _cols_to_host(self, partial_t):
-        """partial (nP,) device vector -> numpy (all-reduce over ranks)."""
-        self._dev
-        return self._coll.all_reduce_sum(partial_t).cpu().numpy()
+        return self._ops.cols_to_host(partial_t)
 
     def _local_rows_of(self, vector):
-        """full (nD,) host vector -> local rows on the device."""
-        dev = self._dev
-        v = dev.to_device(vector, n=self._sharding.nD)
-        if self._coll.world_size == 1:
-            return v
-        return v[self._local_rows_t].contiguous()
+        return self._ops.local_rows_of(vector)
 
     # the four private methods of the reference, on the GPU -------------------------
     def _forward(self, model):
         """G @ model without storing G (gravity/simulation.py:541-583, mag 829-929)."""
-        dev = self._dev
-        fields = dev.forward_dev(dev.to_device(model, n=self._n_columns()))
-        return self._rows_to_host(fields)
+        return self._ops.forward(model)
 
     def _sensitivity_matrix(self):
         """Build the local block of G on the device (gravity/simulation.py:585-629)."""
@@ -301,49 +353,35 @@ class BasePFSimulation:
 
     def _sensitivity_matrix_transpose_dot_vec(self, vector):
         """G.T @ v without storing G (gravity/simulation.py:631-671)."""
-        dev = self._dev
-        return self._cols_to_host(dev.gt_dot_v_dev(self._local_rows_of(vector)))
+        return self._ops.gt_dot_v(vector)
 
     def _gtg_diagonal_without_building_g(self, weights):
         """diag(G.T W.T W G) without storing G (gravity/simulation.py:690-724)."""
-        dev = self._dev
-        return self._cols_to_host(dev.gtg_diag_dev(self._local_rows_of(weights)))
-
-    # stored-G products ---------------------------------------------------------------
-    def _G_matvec(self, x):
-        dev = self._dev
-        return self._rows_to_host(dev.gemv_dev(dev.to_device(x, n=self._n_columns())))
-
-    def _G_rmatvec(self, y):
-        dev = self._dev
-        return self._cols_to_host(dev.gemv_t_dev(self._local_rows_of(y)))
-
-    def _G_to_numpy(self):
-        if self._coll.world_size != 1:
-            raise NotImplementedError("G.to_numpy() is only available on a single process")
-        return self._dev.G_to_numpy()
+        return self._ops.gtg_diag(weights)
 
     def _sensitivity_matrix_as_operator(self):
         """gravity/simulation.py:673-688"""
+        ops = self._ops
         shape = (self.survey.nD, self._n_columns())
-        return DeviceLinearOperator(shape, self._forward,
-                                    self._sensitivity_matrix_transpose_dot_vec)
+        return DeviceLinearOperator(shape, ops.forward, ops.gt_dot_v)
 
     @property
     def G(self):
         """
         Forward operator.  ``engine="cuda"`` always returns a
         :class:`DeviceLinearOperator`; for 'ram' the matrix lives in HBM and is
-        built on first access (gravity/simulation.py:421-443).
+        built on first access (gravity/simulation.py:421-443).  The operator
+        only references the device engine, not the simulation, so dropping both
+        releases the HBM immediately (no reference cycle).
         """
         if not hasattr(self, "_G"):
             if self.store_sensitivities == "forward_only":
                 self._G = self._sensitivity_matrix_as_operator()
             else:
                 self._sensitivity_matrix()
+                ops = self._ops
                 shape = (self.survey.nD, self._n_columns())
-                self._G = DeviceLinearOperator(shape, self._G_matvec, self._G_rmatvec,
-                                               self._G_to_numpy)
+                self._G = DeviceLinearOperator(shape, ops.gemv, ops.gemv_t, ops.G_to_numpy)
         return self._G
 
     def _warn_n_processes(self, kwargs, what):
