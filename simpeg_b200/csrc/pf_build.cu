@@ -1,29 +1,34 @@
 // pf_build.cu -- the FP64-bound kernels of the hot path: per-(receiver, prism)
 // closed-form kernel evaluation with four sinks (store G / forward / G^T v /
 // diag(G^T W G)).  Compiled with -fmad=false so that the kernel arguments, the
-// radius and the 8-vertex sums round exactly like the reference's numba code
-// (which never contracts to FMA).
+// radius and the 8-vertex sums round like the reference's numba code (which
+// never contracts to FMA); the explicit fma() calls of
+// pf_math.cuh are unaffected.
 //
 // Execution model (one CTA = one tile of <=512 cells x one chunk of receivers):
 //   - the tile's node coordinates, the cells' 8 local node ids and their G
 //     columns are loaded ONCE into registers;
 //   - for every receiver of the chunk:
 //       phase 1  each thread evaluates the closed-form kernels on <=3 tile
-//                nodes (atan/log/sqrt in fp64) and writes the needed node
-//                quantities as planes in shared memory  -- this is the
-//                reference's per-receiver `kernels` array
-//                (gravity/_numba/_3d_mesh.py:147-157), at tile granularity;
+//                nodes (pf_math.cuh: 1 sqrt, 3 atan, 3 log in fp64) and writes
+//                one value per OUTPUT PLANE to shared memory.  A plane is a
+//                linear combination of node kernels (a raw kernel, k . f, or
+//                f^T K f): because the 8-vertex sum is linear, the per-cell
+//                algebra of the reference (magnetics/_numba/_3d_mesh.py:
+//                344-372) is hoisted to the nodes, so that phase 2 gathers
+//                8 values per output instead of 8 per kernel;
 //       phase 2  each thread combines the 8 vertices of its <=2 cells with the
 //                reference's sign pattern and order (_numba_utils.py:18-45),
-//                applies the per-component algebra and feeds the sink.
+//                scales and feeds the sink.
 //   - nothing is communicated between CTAs; column/row partial sums go to a
 //     workspace and are reduced in a fixed order (deterministic, no atomics).
 #include "pf_common.cuh"
+#include "pf_math.cuh"
 
 namespace {
 
 // ---------------------------------------------------------------------------
-// node quantities
+// node kernels ("raw" quantities) and output planes
 // ---------------------------------------------------------------------------
 // family 12: first + second order kernels (3 atan + 3 log primitives)
 enum { Q_EE = 0, Q_NN, Q_UU, Q_EN, Q_EU, Q_NU, Q_E, Q_N, Q_U, Q_UV };
@@ -33,16 +38,29 @@ enum { T_EEE = 0, T_NNN, T_UUU, T_EEN, T_EEU, T_ENN, T_NNU, T_EUU, T_NUU, T_ENU 
 enum { NEED_AEE = 1, NEED_ANN = 2, NEED_AUU = 4, NEED_LEN = 8, NEED_LEU = 16, NEED_LNU = 32 };
 
 enum { CT_SINGLE = 0, CT_MAG3 = 1, CT_TMI6 = 2 };
+enum { PK_RAW = 0, PK_DOT3 = 1, PK_QUAD = 2 };
 enum { SINK_STORE = 0, SINK_FORWARD = 1, SINK_GTV = 2, SINK_DIAG = 3 };
+enum { PROG_GENERIC = 0, PROG_TMI = 1 };
 
-constexpr int MAX_SLOTS = 10;
-constexpr int MAX_DESC = PF_MAX_COMPONENTS;
+constexpr int MAX_PLANES = 10;
+constexpr int MAX_OUT = 32;
 constexpr int WARPS = PF_THREADS / 32;
 
-struct CompDesc {
-    int type;     // CT_*
-    int ci;       // position in the receiver object's component list
-    int slot[6];  // shared-memory planes holding the node quantities it needs
+// value stored per (receiver, node):  RAW: k[q0];  DOT3: k[q0] fx + k[q1] fy + k[q2] fz;
+// QUAD: f^T K f with K = (xx, yy, zz, xy, xz, yz) = k[q0..q5]
+struct PlaneDesc {
+    int kind;
+    int q[6];
+};
+
+// G[row(ci), col + blk * nC] = factor * vertex_sum(plane)
+struct OutDesc {
+    int plane;
+    int ci;    // position in the receiver object's component list (row)
+    int blk;   // column block (0 for scalar models, 0..2 for vector models)
+    int fi;    // index of the component inside this launch (forward partial sums)
+    int last;  // last output of its component
+    int pad;
     double factor;  // gravity: G_newton * unit factor; magnetics: (1/4pi) * |B0|
 };
 
@@ -53,12 +71,14 @@ struct LaunchParams {
     int rc;            // receivers per chunk (blockIdx.y)
     int n_comp_total;  // components of the receiver object (row stride)
     int64_t row_offset;
-    int n_desc;
-    int n_slots;
-    int need;          // family-12 primitive mask
+    int n_planes;
+    int n_out;
+    int n_fwd;         // components handled by this launch
+    int need;          // family-12 primitive mask / family-3 kernel mask
     int nblk;          // 1 (gravity, scalar) or 3 (vector model)
-    int slot_q[MAX_SLOTS];
-    CompDesc desc[MAX_DESC];
+    int pad;
+    PlaneDesc planes[MAX_PLANES];
+    OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
     // sinks
     void *G;
@@ -68,102 +88,126 @@ struct LaunchParams {
     double *partial;      // workspace
 };
 
-// ---------------------------------------------------------------------------
-// choclo restatement (device).  Same formulas and operation order as
-// oracle/pf_oracle.c; see DESIGN.md for the provenance of each formula.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double safe_atan2(double y, double x)
+struct Raw10 {
+    double v0, v1, v2, v3, v4, v5, v6, v7, v8, v9;
+};
+
+__device__ __forceinline__ double pick(const Raw10 &k, int q)
 {
-    // choclo._utils._safe_atan2: arctan(y/x); +-pi/2 (0) when x == 0
-    const double half_pi = 1.5707963267948966;
-    double res = atan(y / x);
-    if (x == 0.0) res = (y > 0.0) ? half_pi : ((y < 0.0) ? -half_pi : 0.0);
-    return res;
+    switch (q) {
+    case 0: return k.v0;
+    case 1: return k.v1;
+    case 2: return k.v2;
+    case 3: return k.v3;
+    case 4: return k.v4;
+    case 5: return k.v5;
+    case 6: return k.v6;
+    case 7: return k.v7;
+    case 8: return k.v8;
+    default: return k.v9;
+    }
 }
 
-__device__ __forceinline__ double safe_log(double x, double y, double z, double r)
-{
-    // choclo._utils._safe_log: log(x + r), evaluated as
-    // log((y^2+z^2)/(r-x)) for x<0 and -log(-2x) on the axis (r == -x).
-    // One log call on a selected argument keeps the warp convergent.
-    const bool neg = x < 0.0;
-    const bool axis = neg && (r == -x);
-    double arg = x + r;
-    if (neg) arg = (y * y + z * z) / (r - x);
-    if (axis) arg = -2 * x;
-    double res = log(arg);
-    if (axis) res = -res;
-    if (r == 0.0) res = 0.0;
-    return res;
-}
-
+// choclo.prism third-order kernels (restated, see oracle/pf_oracle.c)
 __device__ __forceinline__ double kernel_iii(double xi, double xj, double xk, double r)
 {
-    if ((xi == 0.0 && xj == 0.0) || (xi == 0.0 && xk == 0.0)) return 0.0;
     double xi2 = xi * xi, xj2 = xj * xj, xk2 = xk * xk;
     double numerator = -xj * xk * (2 * xi2 + xj2 + xk2);
     double denominator = (xi2 + xj2) * (xi2 + xk2) * r;
-    return numerator / denominator;
+    double res = pf_div(numerator, denominator);
+    if ((xi == 0.0 && xj == 0.0) || (xi == 0.0 && xk == 0.0)) res = 0.0;
+    return res;
 }
 
 __device__ __forceinline__ double kernel_iij(double xi, double xj, double xk, double r)
 {
-    if (xi == 0.0 && xj == 0.0 && xk < 0.0) return 0.0;
-    return -xi / ((xk + r) * r);
+    double res = pf_div(-xi, (xk + r) * r);
+    if (xi == 0.0 && xj == 0.0 && xk < 0.0) res = 0.0;
+    return res;
 }
 
-// Evaluate the requested node quantities of one (receiver, node) pair and
-// store them in their planes.
+// Node kernels of one (receiver, node) pair.
 template <int FAM>
-__device__ __forceinline__ void eval_node(const LaunchParams &p, double e, double n, double u,
-                                          double *planes, int j)
+__device__ __forceinline__ void eval_raw(int need, double e, double n, double u, Raw10 &k)
 {
     // gravity/_numba/_3d_mesh.py:494-498: distance = sqrt(dx**2 + dy**2 + dz**2)
     const double r = sqrt(e * e + n * n + u * u);
     if (FAM == 12) {
-        const int need = p.need;
         double Aee = 0, Ann = 0, Auu = 0, Len = 0, Leu = 0, Lnu = 0;
-        if (need & NEED_AEE) Aee = safe_atan2(n * u, e * r);
-        if (need & NEED_ANN) Ann = safe_atan2(e * u, n * r);
-        if (need & NEED_AUU) Auu = safe_atan2(e * n, u * r);
-        if (need & NEED_LEN) Len = safe_log(u, e, n, r);
-        if (need & NEED_LEU) Leu = safe_log(n, e, u, r);
-        if (need & NEED_LNU) Lnu = safe_log(e, n, u, r);
-        for (int s = 0; s < p.n_slots; ++s) {
-            double val;
-            switch (p.slot_q[s]) {
-            case Q_EE: val = -Aee; break;
-            case Q_NN: val = -Ann; break;
-            case Q_UU: val = -Auu; break;
-            case Q_EN: val = Len; break;
-            case Q_EU: val = Leu; break;
-            case Q_NU: val = Lnu; break;
-            // choclo.prism.kernel_e / kernel_n / kernel_u
-            case Q_E: val = -(n * Len + u * Leu - e * Aee); break;
-            case Q_N: val = -(u * Lnu + e * Len - n * Ann); break;
-            case Q_U: val = -(e * Leu + n * Lnu - u * Auu); break;
-            // gravity/simulation.py:23-30 kernel_uv = 0.5 (kernel_nn - kernel_ee)
-            default: val = 0.5 * ((-Ann) - (-Aee)); break;
-            }
-            planes[s * PF_TILE_NODES + j] = val;
-        }
+        if (need & NEED_AEE) Aee = pf_safe_atan2(n * u, e * r);
+        if (need & NEED_ANN) Ann = pf_safe_atan2(e * u, n * r);
+        if (need & NEED_AUU) Auu = pf_safe_atan2(e * n, u * r);
+        if (need & NEED_LEN) Len = pf_safe_log(u, e, n, r);
+        if (need & NEED_LEU) Leu = pf_safe_log(n, e, u, r);
+        if (need & NEED_LNU) Lnu = pf_safe_log(e, n, u, r);
+        k.v0 = -Aee;  // kernel_ee
+        k.v1 = -Ann;  // kernel_nn
+        k.v2 = -Auu;  // kernel_uu
+        k.v3 = Len;   // kernel_en
+        k.v4 = Leu;   // kernel_eu
+        k.v5 = Lnu;   // kernel_nu
+        // choclo.prism.kernel_e / kernel_n / kernel_u
+        k.v6 = -(n * Len + u * Leu - e * Aee);
+        k.v7 = -(u * Lnu + e * Len - n * Ann);
+        k.v8 = -(e * Leu + n * Lnu - u * Auu);
+        // gravity/simulation.py:23-30 kernel_uv = 0.5 (kernel_nn - kernel_ee)
+        k.v9 = 0.5 * ((-Ann) - (-Aee));
     } else {
-        for (int s = 0; s < p.n_slots; ++s) {
-            double val;
-            switch (p.slot_q[s]) {
-            case T_EEE: val = kernel_iii(e, n, u, r); break;
-            case T_NNN: val = kernel_iii(n, u, e, r); break;
-            case T_UUU: val = kernel_iii(u, e, n, r); break;
-            case T_EEN: val = kernel_iij(e, n, u, r); break;
-            case T_EEU: val = kernel_iij(e, u, n, r); break;
-            case T_ENN: val = kernel_iij(n, e, u, r); break;
-            case T_NNU: val = kernel_iij(n, u, e, r); break;
-            case T_EUU: val = kernel_iij(u, e, n, r); break;
-            case T_NUU: val = kernel_iij(u, n, e, r); break;
-            default: val = (r == 0.0) ? 0.0 : -1.0 / r; break;  // kernel_enu
-            }
-            planes[s * PF_TILE_NODES + j] = val;
+        k.v0 = k.v1 = k.v2 = k.v3 = k.v4 = k.v5 = k.v6 = k.v7 = k.v8 = k.v9 = 0.0;
+        if (need & (1 << T_EEE)) k.v0 = kernel_iii(e, n, u, r);
+        if (need & (1 << T_NNN)) k.v1 = kernel_iii(n, u, e, r);
+        if (need & (1 << T_UUU)) k.v2 = kernel_iii(u, e, n, r);
+        if (need & (1 << T_EEN)) k.v3 = kernel_iij(e, n, u, r);
+        if (need & (1 << T_EEU)) k.v4 = kernel_iij(e, u, n, r);
+        if (need & (1 << T_ENN)) k.v5 = kernel_iij(n, e, u, r);
+        if (need & (1 << T_NNU)) k.v6 = kernel_iij(n, u, e, r);
+        if (need & (1 << T_EUU)) k.v7 = kernel_iij(u, e, n, r);
+        if (need & (1 << T_NUU)) k.v8 = kernel_iij(u, n, e, r);
+        if (need & (1 << T_ENU)) {
+            k.v9 = -pf_div(1.0, r);  // kernel_enu
+            if (r == 0.0) k.v9 = 0.0;
         }
+    }
+}
+
+// Evaluate the output planes of one (receiver, node) pair.
+template <int FAM, int PROG>
+__device__ __forceinline__ void eval_node(const LaunchParams &p, double e, double n, double u,
+                                          double *planes, int j)
+{
+    Raw10 k;
+    eval_raw<FAM>(p.need, e, n, u, k);
+    const double fx = p.fx, fy = p.fy, fz = p.fz;
+    if (PROG == PROG_TMI) {
+        // one component "tmi" (magnetics/_numba/_3d_mesh.py:352-372), hoisted to the node
+        const double bx = k.v0 * fx + k.v3 * fy + k.v4 * fz;
+        const double by = k.v3 * fx + k.v1 * fy + k.v5 * fz;
+        const double bz = k.v4 * fx + k.v5 * fy + k.v2 * fz;
+        if (p.nblk == 1) {
+            planes[j] = bx * fx + by * fy + bz * fz;
+        } else {
+            planes[j] = bx;
+            planes[PF_TILE_NODES + j] = by;
+            planes[2 * PF_TILE_NODES + j] = bz;
+        }
+        return;
+    }
+    for (int s = 0; s < p.n_planes; ++s) {
+        const PlaneDesc &pd = p.planes[s];
+        double val;
+        if (pd.kind == PK_RAW) {
+            val = pick(k, pd.q[0]);
+        } else if (pd.kind == PK_DOT3) {
+            val = pick(k, pd.q[0]) * fx + pick(k, pd.q[1]) * fy + pick(k, pd.q[2]) * fz;
+        } else {
+            const double kxx = pick(k, pd.q[0]), kyy = pick(k, pd.q[1]), kzz = pick(k, pd.q[2]);
+            const double kxy = pick(k, pd.q[3]), kxz = pick(k, pd.q[4]), kyz = pick(k, pd.q[5]);
+            const double bx = kxx * fx + kxy * fy + kxz * fz;
+            const double by = kxy * fx + kyy * fy + kyz * fz;
+            const double bz = kxz * fx + kyz * fy + kzz * fz;
+            val = bx * fx + by * fy + bz * fz;
+        }
+        planes[s * PF_TILE_NODES + j] = val;
     }
 }
 
@@ -176,45 +220,6 @@ __device__ __forceinline__ double vertex_sum(const double *pl, const uint4 ci)
     return -pl[i0] + pl[i1] + pl[i2] - pl[i3] + pl[i4] - pl[i5] - pl[i6] + pl[i7];
 }
 
-// Per-cell, per-component algebra.  Returns g[0..nblk).
-__device__ __forceinline__ void cell_component(const LaunchParams &p, const CompDesc &d,
-                                               const double *planes, const uint4 ci,
-                                               double &g0, double &g1, double &g2)
-{
-    g1 = 0.0;
-    g2 = 0.0;
-    if (d.type == CT_SINGLE) {
-        // gravity/_numba/_3d_mesh.py:159-163
-        g0 = d.factor * vertex_sum(planes + d.slot[0] * PF_TILE_NODES, ci);
-        return;
-    }
-    double bx, by, bz;
-    if (d.type == CT_MAG3) {
-        // magnetics/_numba/_3d_mesh.py:182-187
-        bx = vertex_sum(planes + d.slot[0] * PF_TILE_NODES, ci);
-        by = vertex_sum(planes + d.slot[1] * PF_TILE_NODES, ci);
-        bz = vertex_sum(planes + d.slot[2] * PF_TILE_NODES, ci);
-    } else {
-        // magnetics/_numba/_3d_mesh.py:344-354
-        const double uxx = vertex_sum(planes + d.slot[0] * PF_TILE_NODES, ci);
-        const double uyy = vertex_sum(planes + d.slot[1] * PF_TILE_NODES, ci);
-        const double uzz = vertex_sum(planes + d.slot[2] * PF_TILE_NODES, ci);
-        const double uxy = vertex_sum(planes + d.slot[3] * PF_TILE_NODES, ci);
-        const double uxz = vertex_sum(planes + d.slot[4] * PF_TILE_NODES, ci);
-        const double uyz = vertex_sum(planes + d.slot[5] * PF_TILE_NODES, ci);
-        bx = uxx * p.fx + uxy * p.fy + uxz * p.fz;
-        by = uxy * p.fx + uyy * p.fy + uyz * p.fz;
-        bz = uxz * p.fx + uyz * p.fy + uzz * p.fz;
-    }
-    if (p.nblk == 1) {
-        g0 = d.factor * (bx * p.fx + by * p.fy + bz * p.fz);
-    } else {
-        g0 = d.factor * bx;
-        g1 = d.factor * by;
-        g2 = d.factor * bz;
-    }
-}
-
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -222,12 +227,12 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-template <int FAM, int SINK, typename GT>
+template <int FAM, int PROG, int SINK, typename GT>
 __global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ double smem[];
-    double *planes = smem;                                      // [n_slots][TN]
-    double *wpart = smem + (size_t)p.n_slots * PF_TILE_NODES;   // [WARPS][n_desc] (forward)
+    double *planes = smem;                                       // [n_planes][TN]
+    double *wpart = smem + (size_t)p.n_planes * PF_TILE_NODES;   // [WARPS][n_fwd] (forward)
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -269,58 +274,56 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_con
         const double ry = __ldg(p.receivers + 3 * r + 1);
         const double rz = __ldg(p.receivers + 3 * r + 2);
 
-        // ---- phase 1: node quantities -> shared memory planes ---------------
-#pragma unroll
+        // ---- phase 1: output planes of the tile nodes -> shared memory -------
+#pragma unroll 1
         for (int k = 0; k < PF_NPT; ++k) {
             const int j = tid + k * PF_THREADS;
-            if (j < nn) eval_node<FAM>(p, nx[k] - rx, ny[k] - ry, nz[k] - rz, planes, j);
+            // (static register indexing: PF_NPT is 3)
+            const double x = (k == 0) ? nx[0] : ((k == 1) ? nx[1] : nx[2]);
+            const double y = (k == 0) ? ny[0] : ((k == 1) ? ny[1] : ny[2]);
+            const double z = (k == 0) ? nz[0] : ((k == 1) ? nz[1] : nz[2]);
+            if (j < nn) eval_node<FAM, PROG>(p, x - rx, y - ry, z - rz, planes, j);
         }
         __syncthreads();
 
         // ---- phase 2: cells ---------------------------------------------------
-        for (int d = 0; d < p.n_desc; ++d) {
-            const CompDesc &cd = p.desc[d];
-            const int64_t row = p.row_offset + r * p.n_comp_total + cd.ci;
+        double fsum = 0.0;
+        for (int o = 0; o < p.n_out; ++o) {
+            const OutDesc &od = p.outs[o];
+            const double *pl = planes + od.plane * PF_TILE_NODES;
+            const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
             double rowval = 0.0;  // v[row] or w[row]
             if (SINK == SINK_GTV || SINK == SINK_DIAG) rowval = __ldg(p.vec + row);
-            double fsum = 0.0;
 #pragma unroll
             for (int s = 0; s < PF_CPT; ++s) {
                 if (col[s] < 0) continue;
-                double g0, g1, g2;
-                cell_component(p, cd, planes, cidx[s], g0, g1, g2);
+                // gravity/_numba/_3d_mesh.py:159-163: constant_factor * vertex sum
+                const double g = od.factor * vertex_sum(pl, cidx[s]);
                 if (SINK == SINK_STORE) {
-                    GT *grow = reinterpret_cast<GT *>(p.G) + row * p.ldG + col[s];
-                    grow[0] = (GT)g0;
-                    if (p.nblk == 3) {
-                        grow[nC] = (GT)g1;
-                        grow[2 * nC] = (GT)g2;
-                    }
+                    reinterpret_cast<GT *>(p.G)[row * p.ldG + col[s] + od.blk * nC] = (GT)g;
                 } else if (SINK == SINK_FORWARD) {
-                    fsum += g0 * mdl[s][0] + g1 * mdl[s][1] + g2 * mdl[s][2];
-                } else if (SINK == SINK_GTV) {
-                    acc[s][0] += rowval * g0;
-                    acc[s][1] += rowval * g1;
-                    acc[s][2] += rowval * g2;
+                    const double m = (od.blk == 0) ? mdl[s][0] : ((od.blk == 1) ? mdl[s][1] : mdl[s][2]);
+                    fsum += g * m;
                 } else {
-                    acc[s][0] += rowval * (g0 * g0);
-                    acc[s][1] += rowval * (g1 * g1);
-                    acc[s][2] += rowval * (g2 * g2);
+                    const double t = (SINK == SINK_GTV) ? rowval * g : rowval * (g * g);
+                    if (od.blk == 0) acc[s][0] += t;
+                    else if (od.blk == 1) acc[s][1] += t;
+                    else acc[s][2] += t;
                 }
             }
-            if (SINK == SINK_FORWARD) {
+            if (SINK == SINK_FORWARD && od.last) {
                 fsum = warp_sum(fsum);
-                if ((tid & 31) == 0) wpart[(tid >> 5) * p.n_desc + d] = fsum;
+                if ((tid & 31) == 0) wpart[(tid >> 5) * p.n_fwd + od.fi] = fsum;
+                fsum = 0.0;
             }
         }
         __syncthreads();
-        if (SINK == SINK_FORWARD && tid < p.n_desc) {
+        if (SINK == SINK_FORWARD && tid < p.n_fwd) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) t += wpart[w * p.n_desc + tid];
-            // partial[tile][local row]; local row = r * n_desc_total-of-this-launch...
-            const int64_t n_local = p.n_receivers * p.n_desc;
-            p.partial[tile * n_local + r * p.n_desc + tid] = t;
+            for (int w = 0; w < WARPS; ++w) t += wpart[w * p.n_fwd + tid];
+            const int64_t n_local = p.n_receivers * p.n_fwd;
+            p.partial[tile * n_local + r * p.n_fwd + tid] = t;
         }
     }
 
@@ -339,28 +342,28 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_con
     }
 }
 
-// fields[row_offset + r*n_comp_total + ci[d]] += sum_tiles partial[tile][r*n_desc + d]
+// fields[row_offset + r*n_comp_total + ci[f]] += sum_tiles partial[tile][r*n_fwd + f]
 struct ReduceFwdParams {
     const double *partial;
     int64_t n_tiles;
     int64_t n_receivers;
-    int n_desc;
+    int n_fwd;
     int n_comp_total;
     int64_t row_offset;
-    int ci[MAX_DESC];
+    int ci[PF_MAX_COMPONENTS];
     double *fields;
 };
 
 __global__ void __launch_bounds__(256) pf_reduce_forward_kernel(const __grid_constant__ ReduceFwdParams q)
 {
-    const int64_t n_local = q.n_receivers * q.n_desc;
+    const int64_t n_local = q.n_receivers * q.n_fwd;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local) return;
     double t = 0.0;
     for (int64_t tile = 0; tile < q.n_tiles; ++tile) t += q.partial[tile * n_local + i];
-    const int64_t r = i / q.n_desc;
-    const int d = (int)(i - r * q.n_desc);
-    q.fields[q.row_offset + r * q.n_comp_total + q.ci[d]] += t;
+    const int64_t r = i / q.n_fwd;
+    const int f = (int)(i - r * q.n_fwd);
+    q.fields[q.row_offset + r * q.n_comp_total + q.ci[f]] += t;
 }
 
 // out[k] += sum_chunks partial[chunk][k]
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(256) pf_reduce_columns_kernel(const double *pa
 }
 
 // ---------------------------------------------------------------------------
-// host side: job -> launches
+// host side: job -> passes -> launches
 // ---------------------------------------------------------------------------
 struct CompInfo {
     int family;  // 12 or 3
@@ -394,6 +397,7 @@ bool component_info(int physics, int comp, CompInfo &ci)
         return true;
     };
     if (physics == PF_GRAVITY) {
+        // gravity/simulation.py:74-85 CHOCLO_KERNELS
         switch (comp) {
         case PF_GX: return set(12, CT_SINGLE, {Q_E});
         case PF_GY: return set(12, CT_SINGLE, {Q_N});
@@ -408,6 +412,8 @@ bool component_info(int physics, int comp, CompInfo &ci)
         default: return false;
         }
     }
+    // magnetics/simulation.py:45-103 CHOCLO_KERNELS; tmi: _numba/_3d_mesh.py:337-342
+    // six-kernel sets are ordered (xx, yy, zz, xy, xz, yz)
     switch (comp) {
     case PF_TMI: return set(12, CT_TMI6, {Q_EE, Q_NN, Q_UU, Q_EN, Q_EU, Q_NU});
     case PF_BX: return set(12, CT_MAG3, {Q_EE, Q_EN, Q_EU});
@@ -426,8 +432,9 @@ bool component_info(int physics, int comp, CompInfo &ci)
     }
 }
 
-int need_of_quantity(int q)
+int need_of_quantity(int family, int q)
 {
+    if (family == 3) return 1 << q;
     switch (q) {
     case Q_EE: return NEED_AEE;
     case Q_NN: return NEED_ANN;
@@ -476,56 +483,141 @@ int n_blocks_of(const pf_job *job)
     return (job->physics == PF_MAGNETICS && !job->scalar_model) ? 3 : 1;
 }
 
-// Fill the launch parameters of one family; returns false if the job has no
-// component of that family.
-bool fill_family(const pf_plan *plan, const pf_job *job, int family, LaunchParams &p)
+// One pass = one launch of the tile kernel: a subset of the job's components of
+// one kernel family whose output planes fit in shared memory.
+struct Pass {
+    int family;
+    int prog;
+    LaunchParams p;
+};
+
+int find_or_add_plane(LaunchParams &p, int kind, const int *q, int nq)
 {
-    std::memset(&p, 0, sizeof(p));
+    for (int s = 0; s < p.n_planes; ++s) {
+        if (p.planes[s].kind != kind) continue;
+        bool same = true;
+        for (int k = 0; k < nq; ++k) same = same && (p.planes[s].q[k] == q[k]);
+        if (same) return s;
+    }
+    if (p.n_planes == MAX_PLANES) return -1;
+    PlaneDesc &pd = p.planes[p.n_planes];
+    pd.kind = kind;
+    for (int k = 0; k < 6; ++k) pd.q[k] = (k < nq) ? q[k] : 0;
+    return p.n_planes++;
+}
+
+// Try to add component c of the job to the pass; false if it does not fit.
+bool add_component(const pf_job *job, int c, const CompInfo &ci, double amp, LaunchParams &p)
+{
+    const LaunchParams saved = p;
+    const int nblk = p.nblk;
+    double factor;
+    if (job->physics == PF_GRAVITY) {
+        // gravity/simulation.py:101-111 and 580: constants.G * conversion_factor
+        factor = PF_NEWTON_G * ((job->components[c] <= PF_GZ) ? 1e8 : 1e12);
+    } else {
+        // magnetics/simulation.py:958 constant_factor = 1/4/pi, times |B0|
+        factor = (1.0 / 4.0 / 3.141592653589793) * amp;
+    }
+    int plane_of_blk[3] = {-1, -1, -1};
+    if (ci.type == CT_SINGLE) {
+        plane_of_blk[0] = find_or_add_plane(p, PK_RAW, ci.q, 1);
+    } else if (ci.type == CT_MAG3) {
+        if (nblk == 1) {
+            plane_of_blk[0] = find_or_add_plane(p, PK_DOT3, ci.q, 3);
+        } else {
+            for (int b = 0; b < 3; ++b) plane_of_blk[b] = find_or_add_plane(p, PK_RAW, &ci.q[b], 1);
+        }
+    } else {
+        const int xx = ci.q[0], yy = ci.q[1], zz = ci.q[2], xy = ci.q[3], xz = ci.q[4], yz = ci.q[5];
+        if (nblk == 1) {
+            plane_of_blk[0] = find_or_add_plane(p, PK_QUAD, ci.q, 6);
+        } else {
+            const int rows[3][3] = {{xx, xy, xz}, {xy, yy, yz}, {xz, yz, zz}};
+            for (int b = 0; b < 3; ++b) plane_of_blk[b] = find_or_add_plane(p, PK_DOT3, rows[b], 3);
+        }
+    }
+    bool ok = (p.n_out + nblk <= MAX_OUT) && (p.n_fwd < PF_MAX_COMPONENTS);
+    for (int b = 0; b < nblk; ++b) ok = ok && (plane_of_blk[b] >= 0);
+    if (!ok) {
+        p = saved;
+        return false;
+    }
+    for (int b = 0; b < nblk; ++b) {
+        OutDesc &od = p.outs[p.n_out++];
+        od.plane = plane_of_blk[b];
+        od.ci = c;
+        od.blk = b;
+        od.fi = p.n_fwd;
+        od.last = (b == nblk - 1);
+        od.pad = 0;
+        od.factor = factor;
+    }
+    p.n_fwd++;
+    for (int k = 0; k < ci.nq; ++k) p.need |= need_of_quantity(ci.family, ci.q[k]);
+    return true;
+}
+
+void init_pass(const pf_plan *plan, const pf_job *job, double amp, Pass &pass, int family)
+{
+    std::memset(&pass, 0, sizeof(pass));
+    pass.family = family;
+    LaunchParams &p = pass.p;
     p.plan = *plan;
     p.receivers = job->receivers;
     p.n_receivers = job->n_receivers;
     p.n_comp_total = job->n_components;
     p.row_offset = job->row_offset;
     p.nblk = n_blocks_of(job);
-    int slot_of_q[16];
-    for (int i = 0; i < 16; ++i) slot_of_q[i] = -1;
-    double amp = 1.0;
     if (job->physics == PF_MAGNETICS) {
         // magnetics/_numba/_3d_mesh.py:165-169
+        p.fx = job->b0[0] / amp;
+        p.fy = job->b0[1] / amp;
+        p.fz = job->b0[2] / amp;
+    }
+}
+
+// Split the job into passes (usually one per kernel family).
+int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_passes)
+{
+    double amp = 1.0;
+    if (job->physics == PF_MAGNETICS) {
         const double fx = job->b0[0], fy = job->b0[1], fz = job->b0[2];
         amp = sqrt(fx * fx + fy * fy + fz * fz);
-        p.fx = fx / amp;
-        p.fy = fy / amp;
-        p.fz = fz / amp;
     }
-    for (int c = 0; c < job->n_components; ++c) {
-        CompInfo ci;
-        component_info(job->physics, job->components[c], ci);
-        if (ci.family != family) continue;
-        CompDesc &d = p.desc[p.n_desc++];
-        d.type = ci.type;
-        d.ci = c;
-        for (int k = 0; k < ci.nq; ++k) {
-            const int q = ci.q[k];
-            if (slot_of_q[q] < 0) {
-                slot_of_q[q] = p.n_slots;
-                p.slot_q[p.n_slots++] = q;
-                if (family == 12) p.need |= need_of_quantity(q);
+    int n = 0;
+    const int families[2] = {12, 3};
+    for (int family : families) {
+        bool open = false;
+        for (int c = 0; c < job->n_components; ++c) {
+            CompInfo ci;
+            component_info(job->physics, job->components[c], ci);
+            if (ci.family != family) continue;
+            if (!open) {
+                if (n == max_passes) return -1;
+                init_pass(plan, job, amp, passes[n], family);
+                open = true;
             }
-            d.slot[k] = slot_of_q[q];
+            if (!add_component(job, c, ci, amp, passes[n].p)) {
+                ++n;
+                if (n == max_passes) return -1;
+                init_pass(plan, job, amp, passes[n], family);
+                if (!add_component(job, c, ci, amp, passes[n].p)) return -1;
+            }
         }
-        if (job->physics == PF_GRAVITY) {
-            // gravity/simulation.py:101-111 and 580: constants.G * conversion_factor
-            const double conv = (job->components[c] <= PF_GZ) ? 1e8 : 1e12;
-            d.factor = PF_NEWTON_G * conv;
-        } else {
-            // magnetics/simulation.py:958 constant_factor = 1/4/pi, times |B0|
-            const double cf = 1.0 / 4.0 / 3.141592653589793;
-            d.factor = cf * amp;
-        }
+        if (open) ++n;
     }
-    return p.n_desc > 0;
+    for (int i = 0; i < n; ++i) {
+        const LaunchParams &p = passes[i].p;
+        passes[i].prog = PROG_GENERIC;
+        if (passes[i].family == 12 && job->physics == PF_MAGNETICS && p.n_fwd == 1 &&
+            job->components[p.outs[0].ci] == PF_TMI)
+            passes[i].prog = PROG_TMI;
+    }
+    return n;
 }
+
+constexpr int MAX_PASSES = 2 * PF_MAX_COMPONENTS;
 
 // receivers per chunk: enough CTAs to fill the machine a few times over
 int choose_rc(int64_t n_tiles, int64_t n_receivers, int64_t max_chunks)
@@ -540,12 +632,12 @@ int choose_rc(int64_t n_tiles, int64_t n_receivers, int64_t max_chunks)
     return (int)rc;
 }
 
-template <int FAM, int SINK, typename GT>
+template <int FAM, int PROG, int SINK, typename GT>
 int launch_tile_kernel(const LaunchParams &p, cudaStream_t stream)
 {
-    const size_t smem = ((size_t)p.n_slots * PF_TILE_NODES + (SINK == SINK_FORWARD ? WARPS * p.n_desc : 0))
+    const size_t smem = ((size_t)p.n_planes * PF_TILE_NODES + (SINK == SINK_FORWARD ? WARPS * p.n_fwd : 0))
                         * sizeof(double);
-    auto kernel = pf_tile_kernel<FAM, SINK, GT>;
+    auto kernel = pf_tile_kernel<FAM, PROG, SINK, GT>;
     PF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunks = pf_ceil_div(p.n_receivers, p.rc);
     PF_CHECK_ARG(chunks <= 65535, "too many receiver chunks");
@@ -557,13 +649,14 @@ int launch_tile_kernel(const LaunchParams &p, cudaStream_t stream)
 }
 
 template <int SINK, typename GT>
-int launch_family(int family, const LaunchParams &p, cudaStream_t stream)
+int launch_pass(const Pass &pass, cudaStream_t stream)
 {
-    if (family == 12) return launch_tile_kernel<12, SINK, GT>(p, stream);
-    return launch_tile_kernel<3, SINK, GT>(p, stream);
+    if (pass.family == 12) {
+        if (pass.prog == PROG_TMI) return launch_tile_kernel<12, PROG_TMI, SINK, GT>(pass.p, stream);
+        return launch_tile_kernel<12, PROG_GENERIC, SINK, GT>(pass.p, stream);
+    }
+    return launch_tile_kernel<3, PROG_GENERIC, SINK, GT>(pass.p, stream);
 }
-
-const int FAMILIES[2] = {12, 3};
 
 }  // namespace
 
@@ -585,14 +678,16 @@ extern "C" int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64
     if (plan->n_tiles == 0 || job->n_receivers == 0) return PF_OK;
     PF_CHECK_ARG(G != nullptr, "null G");
     PF_CHECK_ARG(ldG >= pf_job_columns(plan, job), "ldG smaller than the number of columns");
-    for (int family : FAMILIES) {
-        LaunchParams p;
-        if (!fill_family(plan, job, family, p)) continue;
+    static thread_local Pass passes[MAX_PASSES];
+    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
+    for (int i = 0; i < n; ++i) {
+        LaunchParams &p = passes[i].p;
         p.G = G;
         p.ldG = ldG;
         p.rc = choose_rc(plan->n_tiles, job->n_receivers, 65535);
-        st = (g_dtype == PF_F64) ? launch_family<SINK_STORE, double>(family, p, (cudaStream_t)stream)
-                                 : launch_family<SINK_STORE, float>(family, p, (cudaStream_t)stream);
+        st = (g_dtype == PF_F64) ? launch_pass<SINK_STORE, double>(passes[i], (cudaStream_t)stream)
+                                 : launch_pass<SINK_STORE, float>(passes[i], (cudaStream_t)stream);
         if (st != PF_OK) return st;
     }
     return PF_OK;
@@ -615,26 +710,28 @@ extern "C" int pf_forward(const pf_plan *plan, const pf_job *job, const double *
         pf_set_error("pf_forward: workspace too small");
         return PF_ERR_WORKSPACE;
     }
-    for (int family : FAMILIES) {
-        LaunchParams p;
-        if (!fill_family(plan, job, family, p)) continue;
+    static thread_local Pass passes[MAX_PASSES];
+    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
+    for (int i = 0; i < n; ++i) {
+        LaunchParams &p = passes[i].p;
         p.model = model;
         p.partial = (double *)workspace;
         p.rc = choose_rc(plan->n_tiles, job->n_receivers, 65535);
-        st = launch_family<SINK_FORWARD, double>(family, p, (cudaStream_t)stream);
+        st = launch_pass<SINK_FORWARD, double>(passes[i], (cudaStream_t)stream);
         if (st != PF_OK) return st;
         ReduceFwdParams q;
         q.partial = p.partial;
         q.n_tiles = plan->n_tiles;
         q.n_receivers = job->n_receivers;
-        q.n_desc = p.n_desc;
+        q.n_fwd = p.n_fwd;
         q.n_comp_total = job->n_components;
         q.row_offset = job->row_offset;
-        for (int d = 0; d < p.n_desc; ++d) q.ci[d] = p.desc[d].ci;
+        for (int o = 0; o < p.n_out; ++o) q.ci[p.outs[o].fi] = p.outs[o].ci;
         q.fields = fields;
-        const int64_t n_local = job->n_receivers * p.n_desc;
+        const int64_t n_local = job->n_receivers * p.n_fwd;
         pf_reduce_forward_kernel<<<(unsigned)pf_ceil_div(n_local, 256), 256, 0, (cudaStream_t)stream>>>(q);
-    PF_COUNT_LAUNCH();
+        PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;
@@ -664,17 +761,19 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
         pf_set_error("column sink: workspace too small");
         return PF_ERR_WORKSPACE;
     }
-    for (int family : FAMILIES) {
-        LaunchParams p;
-        if (!fill_family(plan, job, family, p)) continue;
+    static thread_local Pass passes[MAX_PASSES];
+    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
+    for (int i = 0; i < n; ++i) {
+        LaunchParams &p = passes[i].p;
         p.vec = vec;
         p.partial = (double *)workspace;
         p.rc = choose_rc(plan->n_tiles, job->n_receivers, MAX_COLUMN_CHUNKS);
-        st = launch_family<SINK, double>(family, p, (cudaStream_t)stream);
+        st = launch_pass<SINK, double>(passes[i], (cudaStream_t)stream);
         if (st != PF_OK) return st;
         pf_reduce_columns_kernel<<<(unsigned)pf_ceil_div(nP, 256), 256, 0, (cudaStream_t)stream>>>(
             p.partial, chunks, nP, out);
-    PF_COUNT_LAUNCH();
+        PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;
