@@ -40,7 +40,8 @@ enum { NEED_AEE = 1, NEED_ANN = 2, NEED_AUU = 4, NEED_LEN = 8, NEED_LEU = 16, NE
 enum { CT_SINGLE = 0, CT_MAG3 = 1, CT_TMI6 = 2 };
 enum { PK_RAW = 0, PK_DOT3 = 1, PK_QUAD = 2 };
 enum { SINK_STORE = 0, SINK_FORWARD = 1, SINK_GTV = 2, SINK_DIAG = 3 };
-enum { PROG_GENERIC = 0, PROG_TMI = 1 };
+// PROG_TMI_*: one component "tmi" (the value is the number of column blocks)
+enum { PROG_GENERIC = 0, PROG_TMI_SCALAR = 1, PROG_TMI_VECTOR = 3 };
 
 constexpr int MAX_PLANES = 10;
 constexpr int MAX_OUT = 32;
@@ -176,14 +177,14 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
                                           double *planes, int j)
 {
     Raw10 k;
-    eval_raw<FAM>(p.need, e, n, u, k);
     const double fx = p.fx, fy = p.fy, fz = p.fz;
-    if (PROG == PROG_TMI) {
+    if (PROG != PROG_GENERIC) {
         // one component "tmi" (magnetics/_numba/_3d_mesh.py:352-372), hoisted to the node
+        eval_raw<12>(NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU, e, n, u, k);
         const double bx = k.v0 * fx + k.v3 * fy + k.v4 * fz;
         const double by = k.v3 * fx + k.v1 * fy + k.v5 * fz;
         const double bz = k.v4 * fx + k.v5 * fy + k.v2 * fz;
-        if (p.nblk == 1) {
+        if (PROG == PROG_TMI_SCALAR) {
             planes[j] = bx * fx + by * fy + bz * fz;
         } else {
             planes[j] = bx;
@@ -192,6 +193,7 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         }
         return;
     }
+    eval_raw<FAM>(p.need, e, n, u, k);
     for (int s = 0; s < p.n_planes; ++s) {
         const PlaneDesc &pd = p.planes[s];
         double val;
@@ -211,13 +213,30 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
     }
 }
 
+// The 8 vertices of a cell as BYTE offsets into a plane (kept in registers for
+// the whole receiver loop).
+struct CellVerts {
+    int o0, o1, o2, o3, o4, o5, o6, o7;
+};
+
+__device__ __forceinline__ CellVerts unpack_verts(const uint4 ci)
+{
+    CellVerts v;
+    v.o0 = (ci.x & 0xffff) * 8; v.o1 = (ci.x >> 16) * 8;
+    v.o2 = (ci.y & 0xffff) * 8; v.o3 = (ci.y >> 16) * 8;
+    v.o4 = (ci.z & 0xffff) * 8; v.o5 = (ci.z >> 16) * 8;
+    v.o6 = (ci.w & 0xffff) * 8; v.o7 = (ci.w >> 16) * 8;
+    return v;
+}
+
 // _numba_utils.py:18-45 kernels_in_nodes_to_cell: -k0+k1+k2-k3+k4-k5-k6+k7,
 // evaluated left to right.
-__device__ __forceinline__ double vertex_sum(const double *pl, const uint4 ci)
+__device__ __forceinline__ double vertex_sum(const char *plane, const CellVerts &v)
 {
-    const int i0 = ci.x & 0xffff, i1 = ci.x >> 16, i2 = ci.y & 0xffff, i3 = ci.y >> 16;
-    const int i4 = ci.z & 0xffff, i5 = ci.z >> 16, i6 = ci.w & 0xffff, i7 = ci.w >> 16;
-    return -pl[i0] + pl[i1] + pl[i2] - pl[i3] + pl[i4] - pl[i5] - pl[i6] + pl[i7];
+#define PF_AT(o) (*reinterpret_cast<const double *>(plane + (o)))
+    return -PF_AT(v.o0) + PF_AT(v.o1) + PF_AT(v.o2) - PF_AT(v.o3) + PF_AT(v.o4) - PF_AT(v.o5)
+           - PF_AT(v.o6) + PF_AT(v.o7);
+#undef PF_AT
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -227,47 +246,45 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+constexpr int PLANE_BYTES = PF_TILE_NODES * 8;
+
 template <int FAM, int PROG, int SINK, typename GT>
 __global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ double smem[];
-    double *planes = smem;                                       // [n_planes][TN]
-    double *wpart = smem + (size_t)p.n_planes * PF_TILE_NODES;   // [WARPS][n_fwd] (forward)
+    double *sxyz = smem;                                         // [3][TN] node coordinates
+    double *planes = smem + 3 * PF_TILE_NODES;                   // [n_planes][TN]
+    double *wpart = planes + (size_t)p.n_planes * PF_TILE_NODES; // [WARPS][n_fwd] (forward)
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
     const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
     const int64_t nC = p.plan.n_cells;
+    const int nblk = (PROG == PROG_GENERIC) ? p.nblk : PROG;
 
-    // ---- tile-stationary state in registers --------------------------------
+    // ---- tile-stationary state ------------------------------------------------
     const int nn = p.plan.tile_n_nodes[tile];
-    double nx[PF_NPT], ny[PF_NPT], nz[PF_NPT];
     const double *xyz = p.plan.tile_xyz + tile * (3 * PF_TILE_NODES);
-#pragma unroll
-    for (int k = 0; k < PF_NPT; ++k) {
-        const int j = tid + k * PF_THREADS;
-        nx[k] = xyz[j];
-        ny[k] = xyz[PF_TILE_NODES + j];
-        nz[k] = xyz[2 * PF_TILE_NODES + j];
-    }
+    for (int i = tid; i < 3 * PF_TILE_NODES; i += PF_THREADS) sxyz[i] = xyz[i];
     int col[PF_CPT];
-    uint4 cidx[PF_CPT];
+    CellVerts verts[PF_CPT];
     double mdl[PF_CPT][3];
     double acc[PF_CPT][3];
 #pragma unroll
     for (int s = 0; s < PF_CPT; ++s) {
         const int64_t slot = tile * PF_TILE_CELLS + tid + s * PF_THREADS;
         col[s] = p.plan.tile_cell_col[slot];
-        cidx[s] = reinterpret_cast<const uint4 *>(p.plan.tile_cell_nodes)[slot];
+        verts[s] = unpack_verts(reinterpret_cast<const uint4 *>(p.plan.tile_cell_nodes)[slot]);
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             acc[s][b] = 0.0;
             mdl[s][b] = 0.0;
-            if (SINK == SINK_FORWARD && col[s] >= 0 && b < p.nblk)
+            if (SINK == SINK_FORWARD && col[s] >= 0 && b < nblk)
                 mdl[s][b] = p.model[col[s] + b * nC];
         }
     }
+    __syncthreads();
 
     for (int64_t r = r_begin; r < r_end; ++r) {
         const double rx = __ldg(p.receivers + 3 * r);
@@ -276,45 +293,68 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_con
 
         // ---- phase 1: output planes of the tile nodes -> shared memory -------
 #pragma unroll 1
-        for (int k = 0; k < PF_NPT; ++k) {
-            const int j = tid + k * PF_THREADS;
-            // (static register indexing: PF_NPT is 3)
-            const double x = (k == 0) ? nx[0] : ((k == 1) ? nx[1] : nx[2]);
-            const double y = (k == 0) ? ny[0] : ((k == 1) ? ny[1] : ny[2]);
-            const double z = (k == 0) ? nz[0] : ((k == 1) ? nz[1] : nz[2]);
-            if (j < nn) eval_node<FAM, PROG>(p, x - rx, y - ry, z - rz, planes, j);
-        }
+        for (int j = tid; j < nn; j += PF_THREADS)
+            eval_node<FAM, PROG>(p, sxyz[j] - rx, sxyz[PF_TILE_NODES + j] - ry,
+                                 sxyz[2 * PF_TILE_NODES + j] - rz, planes, j);
         __syncthreads();
 
         // ---- phase 2: cells ---------------------------------------------------
-        double fsum = 0.0;
-        for (int o = 0; o < p.n_out; ++o) {
-            const OutDesc &od = p.outs[o];
-            const double *pl = planes + od.plane * PF_TILE_NODES;
-            const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
-            double rowval = 0.0;  // v[row] or w[row]
+        const char *pbase = reinterpret_cast<const char *>(planes);
+        if (PROG != PROG_GENERIC) {
+            // single component: row = row_offset + r, factor of the only component
+            const int64_t row = p.row_offset + r * p.n_comp_total + p.outs[0].ci;
+            const double factor = p.outs[0].factor;
+            double rowval = 0.0;
             if (SINK == SINK_GTV || SINK == SINK_DIAG) rowval = __ldg(p.vec + row);
+            GT *grow = reinterpret_cast<GT *>(p.G) + row * p.ldG;
+            double fsum = 0.0;
 #pragma unroll
             for (int s = 0; s < PF_CPT; ++s) {
                 if (col[s] < 0) continue;
-                // gravity/_numba/_3d_mesh.py:159-163: constant_factor * vertex sum
-                const double g = od.factor * vertex_sum(pl, cidx[s]);
-                if (SINK == SINK_STORE) {
-                    reinterpret_cast<GT *>(p.G)[row * p.ldG + col[s] + od.blk * nC] = (GT)g;
-                } else if (SINK == SINK_FORWARD) {
-                    const double m = (od.blk == 0) ? mdl[s][0] : ((od.blk == 1) ? mdl[s][1] : mdl[s][2]);
-                    fsum += g * m;
-                } else {
-                    const double t = (SINK == SINK_GTV) ? rowval * g : rowval * (g * g);
-                    if (od.blk == 0) acc[s][0] += t;
-                    else if (od.blk == 1) acc[s][1] += t;
-                    else acc[s][2] += t;
+#pragma unroll
+                for (int b = 0; b < PROG; ++b) {
+                    const double g = factor * vertex_sum(pbase + b * PLANE_BYTES, verts[s]);
+                    if (SINK == SINK_STORE) grow[(unsigned)col[s] + (uint64_t)b * nC] = (GT)g;
+                    else if (SINK == SINK_FORWARD) fsum += g * mdl[s][b];
+                    else if (SINK == SINK_GTV) acc[s][b] += rowval * g;
+                    else acc[s][b] += rowval * (g * g);
                 }
             }
-            if (SINK == SINK_FORWARD && od.last) {
+            if (SINK == SINK_FORWARD) {
                 fsum = warp_sum(fsum);
-                if ((tid & 31) == 0) wpart[(tid >> 5) * p.n_fwd + od.fi] = fsum;
-                fsum = 0.0;
+                if ((tid & 31) == 0) wpart[tid >> 5] = fsum;
+            }
+        } else {
+            double fsum = 0.0;
+            for (int o = 0; o < p.n_out; ++o) {
+                const OutDesc &od = p.outs[o];
+                const char *pl = pbase + od.plane * PLANE_BYTES;
+                const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
+                double rowval = 0.0;  // v[row] or w[row]
+                if (SINK == SINK_GTV || SINK == SINK_DIAG) rowval = __ldg(p.vec + row);
+                GT *grow = reinterpret_cast<GT *>(p.G) + row * p.ldG + od.blk * nC;
+#pragma unroll
+                for (int s = 0; s < PF_CPT; ++s) {
+                    if (col[s] < 0) continue;
+                    // gravity/_numba/_3d_mesh.py:159-163: constant_factor * vertex sum
+                    const double g = od.factor * vertex_sum(pl, verts[s]);
+                    if (SINK == SINK_STORE) {
+                        grow[(unsigned)col[s]] = (GT)g;
+                    } else if (SINK == SINK_FORWARD) {
+                        const double m = (od.blk == 0) ? mdl[s][0] : ((od.blk == 1) ? mdl[s][1] : mdl[s][2]);
+                        fsum += g * m;
+                    } else {
+                        const double t = (SINK == SINK_GTV) ? rowval * g : rowval * (g * g);
+                        if (od.blk == 0) acc[s][0] += t;
+                        else if (od.blk == 1) acc[s][1] += t;
+                        else acc[s][2] += t;
+                    }
+                }
+                if (SINK == SINK_FORWARD && od.last) {
+                    fsum = warp_sum(fsum);
+                    if ((tid & 31) == 0) wpart[(tid >> 5) * p.n_fwd + od.fi] = fsum;
+                    fsum = 0.0;
+                }
             }
         }
         __syncthreads();
@@ -328,13 +368,13 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_con
     }
 
     if (SINK == SINK_GTV || SINK == SINK_DIAG) {
-        const int64_t nP = nC * p.nblk;
+        const int64_t nP = nC * nblk;
         double *out = p.partial + (int64_t)blockIdx.y * nP;
 #pragma unroll
         for (int s = 0; s < PF_CPT; ++s) {
             if (col[s] < 0) continue;
             out[col[s]] = acc[s][0];
-            if (p.nblk == 3) {
+            if (nblk == 3) {
                 out[col[s] + nC] = acc[s][1];
                 out[col[s] + 2 * nC] = acc[s][2];
             }
@@ -612,7 +652,7 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
         passes[i].prog = PROG_GENERIC;
         if (passes[i].family == 12 && job->physics == PF_MAGNETICS && p.n_fwd == 1 &&
             job->components[p.outs[0].ci] == PF_TMI)
-            passes[i].prog = PROG_TMI;
+            passes[i].prog = (p.nblk == 3) ? PROG_TMI_VECTOR : PROG_TMI_SCALAR;
     }
     return n;
 }
@@ -635,8 +675,8 @@ int choose_rc(int64_t n_tiles, int64_t n_receivers, int64_t max_chunks)
 template <int FAM, int PROG, int SINK, typename GT>
 int launch_tile_kernel(const LaunchParams &p, cudaStream_t stream)
 {
-    const size_t smem = ((size_t)p.n_planes * PF_TILE_NODES + (SINK == SINK_FORWARD ? WARPS * p.n_fwd : 0))
-                        * sizeof(double);
+    const size_t smem = ((size_t)(3 + p.n_planes) * PF_TILE_NODES +
+                         (SINK == SINK_FORWARD ? WARPS * p.n_fwd : 0)) * sizeof(double);
     auto kernel = pf_tile_kernel<FAM, PROG, SINK, GT>;
     PF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunks = pf_ceil_div(p.n_receivers, p.rc);
@@ -652,7 +692,10 @@ template <int SINK, typename GT>
 int launch_pass(const Pass &pass, cudaStream_t stream)
 {
     if (pass.family == 12) {
-        if (pass.prog == PROG_TMI) return launch_tile_kernel<12, PROG_TMI, SINK, GT>(pass.p, stream);
+        if (pass.prog == PROG_TMI_VECTOR)
+            return launch_tile_kernel<12, PROG_TMI_VECTOR, SINK, GT>(pass.p, stream);
+        if (pass.prog == PROG_TMI_SCALAR)
+            return launch_tile_kernel<12, PROG_TMI_SCALAR, SINK, GT>(pass.p, stream);
         return launch_tile_kernel<12, PROG_GENERIC, SINK, GT>(pass.p, stream);
     }
     return launch_tile_kernel<3, PROG_GENERIC, SINK, GT>(pass.p, stream);
