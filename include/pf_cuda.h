@@ -198,6 +198,26 @@ int pf_colsumsq_amp(const void *G, int64_t n_loc, int64_t cols, int64_t ld, int 
                     const double *w, const double *ampderiv, double *d, void *workspace,
                     int64_t workspace_bytes, void *stream);
 
+/*
+ * Host-side tile planner for tensor meshes (HOST pointers; no CUDA calls).
+ * Produces the arrays of pf_plan from the 1-D node coordinates and the list of
+ * active cells (mesh indices, x fastest, ascending; NULL = all active), i.e.
+ * what BasePFSimulation._get_active_nodes (base.py:371-399) feeds the numba
+ * loops with, already cut into bricks of (bx, by, bz) cells.  Call
+ * pf_plan_tensor_count first (it marks the bricks that hold active cells in
+ * `used`, one byte per brick, and returns how many: n_tiles), allocate
+ * tile_xyz[n_tiles][3][768], tile_cell_nodes[n_tiles][512][8],
+ * tile_cell_col[n_tiles][512], tile_n_nodes[n_tiles], then call
+ * pf_plan_tensor_fill.  Column k of G is the k-th active cell.
+ */
+int64_t pf_plan_tensor_count(int64_t nx, int64_t ny, int64_t nz, int64_t bx, int64_t by,
+                             int64_t bz, const int64_t *active, int64_t n_active, uint8_t *used);
+int pf_plan_tensor_fill(int64_t nx, int64_t ny, int64_t nz, const double *xs, const double *ys,
+                        const double *zs, int64_t bx, int64_t by, int64_t bz,
+                        const int64_t *active, int64_t n_active, const uint8_t *used,
+                        int64_t n_tiles, double *tile_xyz, uint16_t *tile_cell_nodes,
+                        int32_t *tile_cell_col, int32_t *tile_n_nodes);
+
 /* FP64 pipe peak probe: runs a dependent-free DFMA loop and returns the
  * achieved FLOP/s (2 per DFMA) in *flops; used by bench.py for the roofline
  * denominator of the compute-bound build kernels. */

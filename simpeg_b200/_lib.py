@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = (
     "pf_gemv_t_workspace_bytes", "pf_gemv_t",
     "pf_colsumsq", "pf_colsumsq_amp",
     "pf_amp_normalize", "pf_amp_combine", "pf_amp_spread",
+    "pf_plan_tensor_count", "pf_plan_tensor_fill",
     "pf_probe_fp64_peak",
 )
 
@@ -109,6 +110,8 @@ def load_library() -> ctypes.CDLL:
         "pf_amp_normalize": (i32, [vp, i64, vp, vp, vp]),
         "pf_amp_combine": (i32, [vp, vp, i64, vp, vp]),
         "pf_amp_spread": (i32, [vp, vp, i64, vp, vp]),
+        "pf_plan_tensor_count": (i64, [i64] * 6 + [vp, i64, vp]),
+        "pf_plan_tensor_fill": (i32, [i64] * 3 + [vp] * 3 + [i64] * 3 + [vp, i64, vp, i64] + [vp] * 4),
         "pf_probe_fp64_peak": (i32, [ctypes.POINTER(dbl), vp]),
     }
     for name, (restype, argtypes) in sigs.items():

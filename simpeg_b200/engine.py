@@ -18,6 +18,7 @@ from . import _lib
 from .tiling import TILE_CELLS, TILE_NODES, TilePlan, build_tile_plan
 
 _G_ALIGN = 16  # leading dimension of G in elements (128 B rows for fp64)
+_PINNED = {"turn": 0, "bufs": [None, None], "events": [None, None]}
 
 
 def _require_cuda():
@@ -124,15 +125,49 @@ class CudaEngine:
             self._ws = self.torch.empty((nbytes + 7) // 8, dtype=self.torch.float64, device=self.device)
         return self._ws
 
+    def _pinned(self, n):
+        """Rotating pair of pinned host staging buffers, shared by all engines of the
+        process (page-locking memory is slow, so they are grown, never freed)."""
+        torch = self.torch
+        st = _PINNED
+        st["turn"] = 1 - st["turn"]
+        i = st["turn"]
+        if st["events"][i] is not None:
+            st["events"][i].synchronize()   # the previous async copy using it is done
+            st["events"][i] = None
+        if st["bufs"][i] is None or st["bufs"][i].numel() < n:
+            st["bufs"][i] = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)
+        return i, st["bufs"][i][:n]
+
     def to_device(self, array, n=None):
+        """host vector -> device, through pinned memory (async on the current stream)."""
         a = np.ascontiguousarray(array, dtype=np.float64).reshape(-1)
         if n is not None and a.shape[0] != n:
             raise ValueError(f"expected a vector of length {n}, got {a.shape[0]}")
-        return self.torch.from_numpy(a).to(self.device, non_blocking=False)
+        torch = self.torch
+        i, pin = self._pinned(a.shape[0])
+        pin.numpy()[:] = a
+        with torch.cuda.device(self.device):
+            dev = torch.empty(a.shape[0], dtype=torch.float64, device=self.device)
+            dev.copy_(pin, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        _PINNED["events"][i] = ev
+        return dev
 
-    @staticmethod
-    def to_host(tensor):
-        return tensor.detach().cpu().numpy()
+    def to_host(self, tensor):
+        """device vector -> new numpy array, through pinned memory."""
+        torch = self.torch
+        t = tensor.detach().reshape(-1)
+        if t.dtype != torch.float64 or t.device.type != "cuda":
+            return t.cpu().numpy()
+        i, pin = self._pinned(t.numel())
+        with torch.cuda.device(self.device):
+            pin.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        ev.synchronize()
+        return pin.numpy().copy()
 
     def _jp(self, job):
         return ctypes.byref(self.plan), ctypes.byref(job)

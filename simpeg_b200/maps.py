@@ -11,11 +11,19 @@ import numpy as np
 import scipy.sparse as sp
 
 
+class IdentityDeriv(sp.csr_matrix):
+    """``sp.identity`` that says so: lets the simulations skip the (host-side,
+    O(nP)) sparse products with the derivative of an identity mapping."""
+
+    is_identity = True
+
+
 class IdentityMap:
     def __init__(self, mesh=None, nP=None):
         if nP is None and mesh is not None:
             nP = mesh.n_cells
         self.nP = nP
+        self._deriv = None
 
     @property
     def shape(self):
@@ -28,9 +36,12 @@ class IdentityMap:
         return self._transform(m)
 
     def deriv(self, m, v=None):
+        if v is not None:
+            return np.asarray(v)
         n = self.nP if self.nP is not None else np.asarray(m).size
-        d = sp.identity(n, format="csr")
-        return d if v is None else d @ v
+        if self._deriv is None or self._deriv.shape[0] != n:
+            self._deriv = IdentityDeriv(sp.identity(n, format="csr"))
+        return self._deriv
 
 
 class ExpMap(IdentityMap):

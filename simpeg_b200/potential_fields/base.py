@@ -88,12 +88,12 @@ class ShardedDeviceOps:
     def rows_to_host(self, local_t):
         """local rows (device) -> full (nD,) numpy vector (all-gather over ranks)."""
         if self.coll.world_size == 1:
-            return local_t.cpu().numpy()
-        return self.coll.all_gather_rows(local_t, self.sharding).cpu().numpy()
+            return self.engine.to_host(local_t)
+        return self.engine.to_host(self.coll.all_gather_rows(local_t, self.sharding))
 
     def cols_to_host(self, partial_t):
         """partial (nP,) device vector -> numpy (all-reduce over ranks)."""
-        return self.coll.all_reduce_sum(partial_t).cpu().numpy()
+        return self.engine.to_host(self.coll.all_reduce_sum(partial_t))
 
     def local_rows_of(self, vector):
         """full (nD,) host vector -> local rows on the device."""
@@ -236,6 +236,10 @@ class BasePFSimulation:
 
     @model.setter
     def model(self, value):
+        if value is not None and value is getattr(self, "_model_src", None) \
+                and not self._delete_on_model_update:
+            return                      # same array object as last time: nothing cached depends on it
+        self._model_src = value
         if value is not None:
             value = np.asarray(value, dtype=np.float64).reshape(-1)
         prev = self._model
@@ -264,6 +268,20 @@ class BasePFSimulation:
         d = mapping.deriv(self._model)
         return d if sp.issparse(d) else sp.csr_matrix(d)
 
+    @staticmethod
+    def _deriv_dot(deriv, v):
+        """deriv @ v, skipping the sparse product for an identity mapping."""
+        if getattr(deriv, "is_identity", False):
+            return np.asarray(v, dtype=np.float64)
+        return np.asarray(deriv @ v, dtype=np.float64)
+
+    @staticmethod
+    def _deriv_t_dot(deriv, v):
+        """deriv.T @ v"""
+        if getattr(deriv, "is_identity", False):
+            return np.asarray(v)
+        return np.asarray(deriv.T @ v)
+
     # ------------------------------------------------------------ mesh -> arrays
     def _get_active_nodes(self):
         """
@@ -287,6 +305,17 @@ class BasePFSimulation:
             cell_nodes = active_cell_nodes.reshape(cell_nodes.shape)
         self._active_nodes_cache = (np.asarray(nodes, dtype=np.float64), cell_nodes)
         return self._active_nodes_cache
+
+    def _tile_plan(self):
+        """Tile plan of the active cells: native O(n) planner for tensor meshes,
+        the generic (nodes, cell_nodes) planner otherwise (tree meshes)."""
+        from ..tiling import build_tile_plan, build_tile_plan_tensor, tensor_axes_of
+
+        axes = tensor_axes_of(self.mesh)
+        if axes is not None:
+            active = None if self.nC == self.mesh.n_cells else np.nonzero(self.active_cells)[0]
+            return build_tile_plan_tensor(axes, active)
+        return build_tile_plan(*self._get_active_nodes())
 
     def _get_components_and_receivers(self):
         """base.py:401-408"""
@@ -313,11 +342,10 @@ class BasePFSimulation:
             receiver_list = [(np.asarray(loc, dtype=np.float64), list(comps))
                              for comps, loc in self._get_components_and_receivers()]
             sharding = ReceiverSharding(receiver_list, coll.rank, coll.world_size)
-            nodes, cell_nodes = self._get_active_nodes()
             engine = CudaEngine(
-                self._physics, nodes, cell_nodes, sharding.local_receiver_list,
+                self._physics, None, None, sharding.local_receiver_list,
                 sensitivity_dtype=self.sensitivity_dtype, device=self._device,
-                **self._engine_kwargs())
+                plan=self._tile_plan(), **self._engine_kwargs())
             self._engine_obj = ShardedDeviceOps(engine, coll, sharding)
         return self._engine_obj
 

@@ -85,14 +85,14 @@ class Simulation3DIntegral(BasePFSimulation):
     def Jvec(self, m, v, f=None):
         """gravity/simulation.py:357-387"""
         self.model = m
-        dmu_dm_v = self.rhoDeriv @ v
-        return np.asarray(self.G @ np.asarray(dmu_dm_v, dtype=np.float64))
+        dmu_dm_v = self._deriv_dot(self.rhoDeriv, v)
+        return np.asarray(self.G @ dmu_dm_v)
 
     def Jtvec(self, m, v, f=None):
         """gravity/simulation.py:389-419"""
         self.model = m
         Jtvec = self.G.T @ np.asarray(v, dtype=np.float64)
-        return np.asarray(self.rhoDeriv.T @ Jtvec)
+        return self._deriv_t_dot(self.rhoDeriv, Jtvec)
 
 
 __all__ = ["Simulation3DIntegral", "LinearOperator"]

@@ -175,7 +175,7 @@ class Simulation3DIntegral(BasePFSimulation):
     def Jvec(self, m, v, f=None):
         """magnetics/simulation.py:459-497"""
         self.model = m
-        dmu_dm_v = np.asarray(self.chiDeriv @ v, dtype=np.float64)
+        dmu_dm_v = self._deriv_dot(self.chiDeriv, v)
         if not self.is_amplitude_data:
             return np.asarray(self.G @ dmu_dm_v)
         dev = self._dev
@@ -195,7 +195,7 @@ class Simulation3DIntegral(BasePFSimulation):
             self.G
             spread = dev.amp_spread_dev(self._amp_deriv_device(), self._local_locations_of(v))
             Jtvec = self._cols_to_host(dev.gemv_t_dev(spread))
-        return np.asarray(self.chiDeriv.T @ Jtvec)
+        return self._deriv_t_dot(self.chiDeriv, Jtvec)
 
     # ------------------------------------------------------- amplitude helpers
     def _check_amplitude_layout(self):
@@ -234,11 +234,11 @@ class Simulation3DIntegral(BasePFSimulation):
         dev = self._dev
         torch = dev.torch
         if self._coll.world_size == 1:
-            return local_t.cpu().numpy()
+            return dev.to_host(local_t)
         # reuse the row all-gather on a 3x interleaved copy (tiny vectors)
         rep = local_t.repeat_interleave(3)
         full = self._coll.all_gather_rows(rep, self._sharding)
-        return full[::3].contiguous().cpu().numpy() if isinstance(full, torch.Tensor) else full[::3]
+        return dev.to_host(full[::3].contiguous())
 
     @property
     def ampDeriv(self):

@@ -82,26 +82,7 @@ def _brick_tile_ids(centers):
     lin = idx[0] + dims[0] * (idx[1] + dims[1] * idx[2])
     if len(np.unique(lin)) != n:
         return None
-    best = None
-    for bx in range(1, 17):
-        for by in range(1, 17):
-            for bz in range(1, 17):
-                if bx * by * bz > TILE_CELLS or (bx + 1) * (by + 1) * (bz + 1) > TILE_NODES:
-                    continue
-                cost = 0
-                # full and remainder bricks along every axis
-                parts = []
-                for d, b in zip(dims, (bx, by, bz)):
-                    full, rem = divmod(d, b)
-                    parts.append([(b, full)] + ([(rem, 1)] if rem else []))
-                for sx, cx in parts[0]:
-                    for sy, cy in parts[1]:
-                        for sz, cz in parts[2]:
-                            cost += cx * cy * cz * _tile_cost(sx * sy * sz, (sx + 1) * (sy + 1) * (sz + 1))
-                key = (cost, -bx)  # prefer long x runs (contiguous G columns)
-                if best is None or key < best[0]:
-                    best = (key, (bx, by, bz))
-    bx, by, bz = best[1]
+    bx, by, bz = _best_brick(dims)
     nbx, nby = -(-dims[0] // bx), -(-dims[1] // by)
     tile = (idx[0] // bx) + nbx * ((idx[1] // by) + nby * (idx[2] // bz))
     return tile
@@ -164,6 +145,91 @@ def _enforce_limits(tile, centers, cell_nodes):
     # compact ids
     _, tile = np.unique(tile, return_inverse=True)
     return tile.astype(np.int64)
+
+
+_BRICK_CACHE = {}
+
+
+def _best_brick(dims):
+    """Brick dimensions minimising the total tile cost for a (nx, ny, nz) grid."""
+    dims = tuple(int(d) for d in dims)
+    if dims in _BRICK_CACHE:
+        return _BRICK_CACHE[dims]
+    best = None
+    for bx in range(1, 17):
+        for by in range(1, 17):
+            for bz in range(1, 17):
+                if bx * by * bz > TILE_CELLS or (bx + 1) * (by + 1) * (bz + 1) > TILE_NODES:
+                    continue
+                parts = []
+                for d, b in zip(dims, (bx, by, bz)):
+                    full, rem = divmod(d, b)
+                    parts.append([(b, full)] + ([(rem, 1)] if rem else []))
+                cost = 0
+                for sx, cx in parts[0]:
+                    for sy, cy in parts[1]:
+                        for sz, cz in parts[2]:
+                            cost += cx * cy * cz * _tile_cost(sx * sy * sz, (sx + 1) * (sy + 1) * (sz + 1))
+                key = (cost, -bx)  # prefer long x runs (contiguous G columns)
+                if best is None or key < best[0]:
+                    best = (key, (bx, by, bz))
+    _BRICK_CACHE[dims] = best[1]
+    return best[1]
+
+
+def build_tile_plan_tensor(axis_nodes, active_index=None) -> TilePlan:
+    """
+    O(n) planner for tensor meshes: pure index arithmetic, done natively by
+    ``pf_plan_tensor_count`` / ``pf_plan_tensor_fill`` (csrc/pf_plan.cu).
+
+    Parameters
+    ----------
+    axis_nodes : (nodes_x, nodes_y, nodes_z) 1-D node coordinates of the mesh
+    active_index : int array of the ACTIVE cells' mesh indices (F-order), ascending,
+        or None when every cell is active.  Column k of G is active cell k.
+    """
+    import ctypes
+
+    from . import _lib
+
+    lib = _lib.load_library()
+    xs, ys, zs = (np.ascontiguousarray(a, dtype=np.float64) for a in axis_nodes)
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
+    act = None if active_index is None else np.ascontiguousarray(active_index, dtype=np.int64)
+    n_cells = nx * ny * nz if act is None else act.size
+    if n_cells == 0:
+        return TilePlan(0, 0, np.zeros((0, 3, TILE_NODES)), np.zeros((0, TILE_CELLS, 8), np.uint16),
+                        np.zeros((0, TILE_CELLS), np.int32), np.zeros(0, np.int32), "empty")
+    if n_cells >= 2**31:
+        raise ValueError("more than 2^31-1 active cells are not supported")
+    bx, by, bz = _best_brick((nx, ny, nz))
+    n_bricks = (-(-nx // bx)) * (-(-ny // by)) * (-(-nz // bz))
+    used = np.zeros(n_bricks, dtype=np.uint8)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    n_act = 0 if act is None else act.size
+    n_tiles = lib.pf_plan_tensor_count(nx, ny, nz, bx, by, bz, ptr(act), n_act, ptr(used))
+    _lib.check(int(min(n_tiles, 0)), "pf_plan_tensor_count")
+    tile_xyz = np.empty((n_tiles, 3, TILE_NODES), dtype=np.float64)
+    tile_cell_nodes = np.zeros((n_tiles, TILE_CELLS, 8), dtype=np.uint16)
+    tile_cell_col = np.empty((n_tiles, TILE_CELLS), dtype=np.int32)
+    tile_n_nodes = np.empty(n_tiles, dtype=np.int32)
+    _lib.check(lib.pf_plan_tensor_fill(nx, ny, nz, ptr(xs), ptr(ys), ptr(zs), bx, by, bz, ptr(act),
+                                       n_act, ptr(used), n_tiles, ptr(tile_xyz), ptr(tile_cell_nodes),
+                                       ptr(tile_cell_col), ptr(tile_n_nodes)), "pf_plan_tensor_fill")
+    return TilePlan(int(n_tiles), int(n_cells), tile_xyz, tile_cell_nodes, tile_cell_col,
+                    tile_n_nodes, "tensor")
+
+
+def tensor_axes_of(mesh):
+    """(nodes_x, nodes_y, nodes_z) if ``mesh`` is a tensor mesh whose ``nodes`` /
+    ``cell_nodes`` follow the F-order convention of base.py:120-141, else None."""
+    if hasattr(mesh, "total_nodes") or not all(
+            hasattr(mesh, a) for a in ("nodes_x", "nodes_y", "nodes_z", "shape_cells")):
+        return None
+    axes = tuple(np.asarray(getattr(mesh, a), dtype=np.float64) for a in ("nodes_x", "nodes_y", "nodes_z"))
+    if tuple(len(a) - 1 for a in axes) != tuple(mesh.shape_cells):
+        return None
+    return axes
 
 
 def build_tile_plan(nodes, cell_nodes, method="auto") -> TilePlan:

@@ -66,6 +66,34 @@ def test_octree_with_hanging_nodes():
     check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb")
 
 
+def _check_tensor_plan(mesh, active=None):
+    from simpeg_b200.tiling import build_tile_plan_tensor, tensor_axes_of
+
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh), active)
+    cn = mesh.cell_nodes if active is None else mesh.cell_nodes[active]
+    cols = plan.tile_cell_col
+    valid = cols >= 0
+    assert np.array_equal(np.sort(cols[valid]), np.arange(cn.shape[0]))
+    tt, ss = np.nonzero(valid)
+    local = plan.tile_cell_nodes[tt, ss]
+    assert (local < plan.tile_n_nodes[tt][:, None]).all()
+    assert np.array_equal(plan.tile_xyz[tt[:, None], :, local], mesh.nodes[cn[cols[tt, ss]]])
+    assert plan.tile_n_nodes.max() <= TILE_NODES
+    return plan
+
+
+def test_native_tensor_planner_matches_mesh_geometry():
+    """pf_plan_tensor_* (csrc/pf_plan.cu): same geometry as nodes[cell_nodes], bit for bit."""
+    mesh = TensorMesh([[(2.0, 3, -1.3), (2.0, 17), (2.0, 3, 1.3)], [(3.0, 13)], [(1.0, 9)]], "CCN")
+    plan = _check_tensor_plan(mesh)
+    assert plan.method == "tensor" and plan.n_cells == mesh.n_cells
+    active = np.nonzero(mesh.cell_centers[:, 2] < -1.0 - 0.1 * np.abs(mesh.cell_centers[:, 0]))[0]
+    plan = _check_tensor_plan(mesh, active)
+    assert plan.n_cells == active.size
+    big = TensorMesh([np.full(40, 5.0), np.full(40, 5.0), np.full(20, 5.0)], "CCN")
+    assert _check_tensor_plan(big).n_tiles == 64
+
+
 def test_empty_and_invalid():
     plan = build_tile_plan(np.zeros((0, 3)), np.zeros((0, 8), dtype=np.int64))
     assert plan.n_tiles == 0
