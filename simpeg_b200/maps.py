@@ -7,6 +7,8 @@ in the reference (gravity/simulation.py:386-387, 418-419).  Any object with
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -18,12 +20,16 @@ class IdentityDeriv(sp.csr_matrix):
     is_identity = True
 
 
+@functools.lru_cache(maxsize=4)
+def _identity_deriv(n):
+    return IdentityDeriv(sp.identity(n, format="csr"))
+
+
 class IdentityMap:
     def __init__(self, mesh=None, nP=None):
         if nP is None and mesh is not None:
             nP = mesh.n_cells
         self.nP = nP
-        self._deriv = None
 
     @property
     def shape(self):
@@ -39,9 +45,7 @@ class IdentityMap:
         if v is not None:
             return np.asarray(v)
         n = self.nP if self.nP is not None else np.asarray(m).size
-        if self._deriv is None or self._deriv.shape[0] != n:
-            self._deriv = IdentityDeriv(sp.identity(n, format="csr"))
-        return self._deriv
+        return _identity_deriv(int(n))
 
 
 class ExpMap(IdentityMap):

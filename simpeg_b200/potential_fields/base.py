@@ -61,6 +61,12 @@ class DeviceLinearOperator(LinearOperator):
     def _rmatvec(self, x):
         return self._rmv(np.asarray(x, dtype=np.float64).reshape(-1))
 
+    # real operator: transpose == adjoint, without scipy's np.conj round trips
+    def _adjoint(self):
+        return DeviceLinearOperator(self.shape[::-1], self._rmv, self._mv)
+
+    _transpose = _adjoint
+
     def to_numpy(self):
         if self._to_numpy is None:
             raise NotImplementedError(
