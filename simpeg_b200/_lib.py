@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libpf_cuda.so"
+import os
+
+# PF_CUDA_LIB: development override (A/B builds of the same ABI)
+LIB_PATH = Path(os.environ.get("PF_CUDA_LIB", Path(__file__).resolve().parent / "libpf_cuda.so"))
 
 PF_MAX_COMPONENTS = 16
 PF_ABI_VERSION = 1

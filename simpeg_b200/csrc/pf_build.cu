@@ -248,8 +248,12 @@ __device__ __forceinline__ double warp_sum(double v)
 
 constexpr int PLANE_BYTES = PF_TILE_NODES * 8;
 
+#ifndef PF_MIN_BLOCKS
+#define PF_MIN_BLOCKS 3
+#endif
+
 template <int FAM, int PROG, int SINK, typename GT>
-__global__ void __launch_bounds__(PF_THREADS, 2) pf_tile_kernel(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ double smem[];
     double *sxyz = smem;                                         // [3][TN] node coordinates

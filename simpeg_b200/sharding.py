@@ -111,10 +111,9 @@ class Collectives:
         """Assemble the full (nD,) vector from every rank's local rows (dpred, Jvec)."""
         import torch
 
-        full = torch.zeros(sharding.nD, dtype=local.dtype, device=local.device)
         if self._dist is None:
-            full[torch.from_numpy(sharding.local_rows).to(local.device)] = local
-            return full
+            return local            # one process owns every row, already in global order
+        full = torch.zeros(sharding.nD, dtype=local.dtype, device=local.device)
         m = sharding.max_local_rows()
         padded = torch.zeros(m, dtype=local.dtype, device=local.device)
         padded[: local.numel()] = local
