@@ -1,0 +1,148 @@
+"""
+GPU: parity at the shapes BASELINE.json names, through (a) the oracle on a
+receiver subsample of the FULL mesh and (b) size-independent properties:
+adjointness <G x, y> = <x, G^T y>, linearity, stored-G vs matrix-free
+agreement, row-block independence (what the multi-GPU sharding relies on),
+tree meshes with hanging nodes, determinism.
+"""
+import numpy as np
+import pytest
+
+from helpers import RTOL_NORMWISE, rowwise_rel, vec_rel
+from oracle.oracle import OracleSimulation
+from simpeg_b200.engine import CudaEngine
+from simpeg_b200.meshes import TensorMesh, synthetic_octree
+from simpeg_b200.tiling import build_tile_plan_tensor, tensor_axes_of
+
+pytestmark = pytest.mark.gpu
+
+B0 = np.array([-8.55e3, -2.35e4, -4.33e4])   # 50 000 nT, I=60, D=250 (test_forward_Mag_Linear.py:214)
+
+
+def grid_receivers(n, half, z, seed):
+    side = int(np.ceil(np.sqrt(n)))
+    xs = np.linspace(-half, half, side)
+    X, Y = np.meshgrid(xs, xs)
+    loc = np.c_[X.ravel(), Y.ravel(), np.full(X.size, z)][:n]
+    loc[:, 2] += np.random.default_rng(seed).uniform(0, 1, n)
+    return loc
+
+
+def tensor_engine(mesh, physics, rlist, **kw):
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh))
+    return CudaEngine(physics, None, None, rlist, plan=plan, **kw)
+
+
+CONFIGS = {
+    # BASELINE configs 1, 2, 3 (mesh shape / spacing / components); receivers subsampled
+    "cfg1_gz": dict(shape=(40, 40, 20), h=5.0, z=1.0, physics="gravity", comps=["gz"], mt="scalar", n_rx=441),
+    "cfg2_tensor7": dict(shape=(100, 100, 50), h=10.0, z=5.0, physics="gravity",
+                         comps=["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"], mt="scalar", n_rx=96),
+    "cfg3_tmi_scalar": dict(shape=(200, 200, 100), h=25.0, z=30.0, physics="magnetics", comps=["tmi"],
+                            mt="scalar", n_rx=64),
+    "cfg4_tmi_vector": dict(shape=(100, 100, 100), h=10.0, z=10.0, physics="magnetics", comps=["tmi"],
+                            mt="vector", n_rx=128),
+}
+
+
+def make(cfg):
+    mesh = TensorMesh([np.full(n, cfg["h"]) for n in cfg["shape"]], "CCN")
+    loc = grid_receivers(cfg["n_rx"], cfg["shape"][0] * cfg["h"] / 2, cfg["z"], 1)
+    eng = tensor_engine(mesh, cfg["physics"], [(loc, cfg["comps"])], b0=B0, model_type=cfg["mt"])
+    return mesh, loc, eng
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_full_mesh_subsample_vs_oracle(name):
+    """G rows / forward / G^T v of a few receivers over the FULL mesh against the oracle."""
+    cfg = CONFIGS[name]
+    mesh, loc, eng = make(cfg)
+    sub = loc[:: max(1, len(loc) // 4)][:4]
+    ora = OracleSimulation(cfg["physics"], mesh.nodes, mesh.cell_nodes, [(sub, cfg["comps"])], b0=B0,
+                           model_type=cfg["mt"])
+    sub_eng = tensor_engine(mesh, cfg["physics"], [(sub, cfg["comps"])], b0=B0, model_type=cfg["mt"])
+    G_ref = ora.sensitivity_matrix()
+    sub_eng.build_G()
+    assert rowwise_rel(sub_eng.G_to_numpy(), G_ref).max() <= RTOL_NORMWISE
+    rng = np.random.default_rng(4)
+    lo, hi = (-0.5, 0.5) if cfg["physics"] == "gravity" else (0.0, 0.05)
+    m = rng.uniform(lo, hi, sub_eng.nP)
+    v = rng.uniform(size=sub_eng.n_rows)
+    assert vec_rel(sub_eng.to_host(sub_eng.forward_dev(sub_eng.to_device(m))), ora.forward(m)) <= RTOL_NORMWISE
+    assert vec_rel(sub_eng.to_host(sub_eng.gt_dot_v_dev(sub_eng.to_device(v))), ora.gt_dot_v(v)) <= RTOL_NORMWISE
+    assert vec_rel(sub_eng.to_host(sub_eng.gemv_dev(sub_eng.to_device(m))), G_ref @ m) <= RTOL_NORMWISE
+    assert vec_rel(sub_eng.to_host(sub_eng.gemv_t_dev(sub_eng.to_device(v))), G_ref.T @ v) <= RTOL_NORMWISE
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_adjoint_linearity_and_store_modes(name):
+    cfg = CONFIGS[name]
+    mesh, loc, eng = make(cfg)
+    rng = np.random.default_rng(9)
+    x1, x2 = eng.to_device(rng.normal(size=eng.nP)), eng.to_device(rng.normal(size=eng.nP))
+    y = eng.to_device(rng.normal(size=eng.n_rows))
+    eng.build_G()
+    Gx1, Gx2 = eng.gemv_dev(x1), eng.gemv_dev(x2)
+    Gty = eng.gemv_t_dev(y)
+    # adjointness of the stored-G products
+    lhs, rhs = float(Gx1 @ y), float(x1 @ Gty)
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs), float(Gx1.norm() * y.norm()))
+    # linearity
+    comb = eng.gemv_dev(2.5 * x1 - 0.75 * x2)
+    assert vec_rel(eng.to_host(comb), eng.to_host(2.5 * Gx1 - 0.75 * Gx2)) <= 1e-11
+    # matrix-free == stored
+    assert vec_rel(eng.to_host(eng.forward_dev(x1)), eng.to_host(Gx1)) <= RTOL_NORMWISE
+    assert vec_rel(eng.to_host(eng.gt_dot_v_dev(y)), eng.to_host(Gty)) <= RTOL_NORMWISE
+    w = eng.to_device(rng.uniform(0.5, 1.5, size=eng.n_rows))
+    assert vec_rel(eng.to_host(eng.gtg_diag_dev(w)), eng.to_host(eng.colsumsq_dev(w))) <= RTOL_NORMWISE
+    # determinism: same bits on a second evaluation
+    assert np.array_equal(eng.to_host(eng.gemv_t_dev(y)), eng.to_host(Gty))
+    assert np.array_equal(eng.to_host(eng.forward_dev(x1)), eng.to_host(eng.forward_dev(x1)))
+
+
+def test_row_blocks_are_independent():
+    """Rows built from a receiver block equal the same rows of the whole build (sharding invariant)."""
+    cfg = CONFIGS["cfg4_tmi_vector"]
+    mesh, loc, eng = make(cfg)
+    eng.build_G()
+    lo, hi = 37, 91
+    part = tensor_engine(mesh, cfg["physics"], [(loc[lo:hi], cfg["comps"])], b0=B0, model_type=cfg["mt"])
+    part.build_G()
+    assert bool((part.G[:, : part.nP] == eng.G[lo:hi, : eng.nP]).all())
+
+
+def test_octree_below_topography():
+    """TreeMesh-style input (hanging nodes, cells of 3 sizes, topography) through the generic planner."""
+    topo = lambda x, y: -12.0 + 10.0 * np.exp(-0.5 * ((x / 60.0) ** 2 + (y / 60.0) ** 2))  # noqa: E731
+    mesh = synthetic_octree((10, 10, 5), 5.0, levels=3, topo=topo)
+    assert mesh.n_cells > 5000 and len(np.unique(np.round(mesh.cell_volumes, 6))) == 3
+    assert mesh.cell_centers[:, 2].max() < -2.0 + 5.0    # cells above the topography were dropped
+    rng = np.random.default_rng(6)
+    xy = rng.uniform(-90, 90, size=(24, 2))
+    loc = np.c_[xy, topo(xy[:, 0], xy[:, 1]) + 5.0]
+    eng = CudaEngine("gravity", mesh.total_nodes, mesh.cell_nodes, [(loc, ["gz", "gzz"])])
+    ora = OracleSimulation("gravity", mesh.total_nodes, mesh.cell_nodes, [(loc, ["gz", "gzz"])])
+    eng.build_G()
+    assert rowwise_rel(eng.G_to_numpy(), ora.sensitivity_matrix()).max() <= RTOL_NORMWISE
+    m = rng.uniform(-0.5, 0.5, eng.nP)
+    w = rng.uniform(0.5, 1.5, eng.n_rows)
+    assert vec_rel(eng.to_host(eng.forward_dev(eng.to_device(m))), ora.forward(m)) <= RTOL_NORMWISE
+    G = ora.sensitivity_matrix()
+    assert vec_rel(eng.to_host(eng.gtg_diag_dev(eng.to_device(w))), np.einsum("i,ij,ij->j", w, G, G)) <= RTOL_NORMWISE
+
+
+def test_physics_sanity_buried_sphere():
+    """Independent known answer: gz of a discretised sphere ~ point mass (gravity/analytics.py:6-86 idea)."""
+    import scipy.constants as constants
+
+    mesh = TensorMesh([np.full(40, 2.5)] * 3, "CCN")
+    centre, radius, drho = np.array([0.0, 0.0, -50.0]), 20.0, 0.5
+    inside = np.linalg.norm(mesh.cell_centers - centre, axis=1) < radius
+    rho = np.where(inside, drho, 0.0)
+    loc = np.array([[0.0, 0.0, 10.0], [30.0, -20.0, 10.0], [80.0, 60.0, 15.0]])
+    eng = tensor_engine(mesh, "gravity", [(loc, ["gz"])])
+    gz = eng.to_host(eng.forward_dev(eng.to_device(rho)))
+    mass = drho * 1e3 * inside.sum() * 2.5**3            # kg (g/cc -> kg/m3)
+    d = centre - loc
+    expected = constants.G * mass * d[:, 2] / np.linalg.norm(d, axis=1) ** 3 * 1e5   # m/s2 -> mGal
+    np.testing.assert_allclose(gz, expected, rtol=2e-3)
