@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 typedef enum {
     PF_OK = 0,
@@ -77,6 +77,28 @@ typedef struct {
     const uint16_t *tile_cell_nodes; /* [n_tiles][TC][8] local node ids, F-order  */
     const int32_t *tile_cell_col;  /* [n_tiles][TC] global cell index, -1 = pad */
     const int32_t *tile_n_nodes;   /* [n_tiles] nodes used in each tile         */
+    /*
+     * Optional tensor-mesh description (grid_nx == 0: absent).  When present,
+     * pf_build_G and pf_forward use the z-marching kernel: a CTA owns an (x, y)
+     * footprint of the mesh and sweeps the node layers bottom-up, keeping the
+     * last two layers of node kernels in shared memory, so that every node is
+     * evaluated once per footprint instead of once per brick.  Cell (ix,iy,iz)
+     * has mesh index ix + nx (iy + ny iz); its G column is colmap[index]
+     * (colmap == NULL: all cells active, column = index; -1 = inactive).
+     * Footprints are given for two node capacities per layer: 1024 ("4") and
+     * 512 ("2") nodes; each is (ix0, iy0, width, height, iz_begin, iz_end): an
+     * (x, y) rectangle of cells with (width + 1)(height + 1) <= capacity and the
+     * range of cell layers [iz_begin, iz_end) that holds its active cells.
+     */
+    int32_t grid_nx, grid_ny, grid_nz;
+    int32_t n_footprints4, n_footprints2;
+    int32_t reserved;
+    const double *grid_xs;         /* [nx+1] node coordinates                   */
+    const double *grid_ys;         /* [ny+1]                                    */
+    const double *grid_zs;         /* [nz+1] ascending                          */
+    const int32_t *grid_colmap;    /* [nx ny nz] or NULL                        */
+    const int32_t *footprints4;    /* [n_footprints4][6]                        */
+    const int32_t *footprints2;    /* [n_footprints2][6]                        */
 } pf_plan;
 
 /*

@@ -4,6 +4,8 @@ import numpy as np, torch
 sys.path.insert(0, ".")
 from simpeg_b200.engine import CudaEngine, probe_fp64_peak
 from simpeg_b200.meshes import TensorMesh
+from simpeg_b200.tiling import build_tile_plan_tensor, tensor_axes_of
+MARCH = '--no-march' not in sys.argv
 
 def timed(fn, n=3):
     torch.cuda.synchronize()
@@ -20,7 +22,8 @@ def run(name, shape, h, n_rx, physics, comps, model_type, dtype=np.float64, z=10
     xs = np.linspace(-shape[0]*h/2, shape[0]*h/2, side); ys = np.linspace(-shape[1]*h/2, shape[1]*h/2, side)
     X, Y = np.meshgrid(xs, ys); rx = np.c_[X.ravel(), Y.ravel(), np.full(X.size, z)][:n_rx]
     t = time.time()
-    eng = CudaEngine(physics, mesh.nodes, mesh.cell_nodes, [(rx, comps)], b0=np.array([1e4,-2e4,-4e4]), model_type=model_type, sensitivity_dtype=dtype)
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh))
+    eng = CudaEngine(physics, None, None, [(rx, comps)], b0=np.array([1e4,-2e4,-4e4]), model_type=model_type, sensitivity_dtype=dtype, plan=plan, use_marching=MARCH)
     tplan = time.time() - t
     pairs = n_rx * eng.nC
     tb = timed(eng.build_G)

@@ -15,7 +15,7 @@ import os
 LIB_PATH = Path(os.environ.get("PF_CUDA_LIB", Path(__file__).resolve().parent / "libpf_cuda.so"))
 
 PF_MAX_COMPONENTS = 16
-PF_ABI_VERSION = 1
+PF_ABI_VERSION = 2
 PF_F64, PF_F32 = 0, 1
 PF_GRAVITY, PF_MAGNETICS = 0, 1
 
@@ -58,6 +58,12 @@ class PfPlan(ctypes.Structure):
         ("tile_cell_nodes", ctypes.c_void_p),
         ("tile_cell_col", ctypes.c_void_p),
         ("tile_n_nodes", ctypes.c_void_p),
+        ("grid_nx", ctypes.c_int32), ("grid_ny", ctypes.c_int32), ("grid_nz", ctypes.c_int32),
+        ("n_footprints4", ctypes.c_int32), ("n_footprints2", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("grid_xs", ctypes.c_void_p), ("grid_ys", ctypes.c_void_p), ("grid_zs", ctypes.c_void_p),
+        ("grid_colmap", ctypes.c_void_p),
+        ("footprints4", ctypes.c_void_p), ("footprints2", ctypes.c_void_p),
     ]
 
 

@@ -47,7 +47,7 @@ class CudaEngine:
 
     def __init__(self, physics, nodes, cell_nodes, receiver_list, b0=None,
                  model_type="scalar", sensitivity_dtype=np.float64, device=None,
-                 plan: TilePlan | None = None):
+                 plan: TilePlan | None = None, use_marching=True):
         torch = _require_cuda()
         self.torch = torch
         self.lib = _lib.load_library()
@@ -78,6 +78,23 @@ class CudaEngine:
             n_tiles=hp.n_tiles, n_cells=hp.n_cells, tile_cells=TILE_CELLS, tile_nodes=TILE_NODES,
             tile_xyz=self._t_xyz.data_ptr(), tile_cell_nodes=self._t_cn.data_ptr(),
             tile_cell_col=self._t_col.data_ptr(), tile_n_nodes=self._t_nn.data_ptr())
+        self.use_marching = bool(use_marching) and hp.grid_shape is not None
+        if self.use_marching:
+            # tensor mesh: enable the z-marching kernel for G build / forward
+            with torch.cuda.device(self.device):
+                self._t_axes = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+                                for a in hp.grid_axes]
+                self._t_colmap = None if hp.grid_colmap is None else \
+                    torch.from_numpy(hp.grid_colmap).to(self.device)
+                self._t_fp4 = torch.from_numpy(hp.footprints4).to(self.device)
+                self._t_fp2 = torch.from_numpy(hp.footprints2).to(self.device)
+            self.plan.grid_nx, self.plan.grid_ny, self.plan.grid_nz = hp.grid_shape
+            self.plan.grid_xs, self.plan.grid_ys, self.plan.grid_zs = (t.data_ptr() for t in self._t_axes)
+            self.plan.grid_colmap = None if self._t_colmap is None else self._t_colmap.data_ptr()
+            self.plan.n_footprints4 = hp.footprints4.shape[0]
+            self.plan.n_footprints2 = hp.footprints2.shape[0]
+            self.plan.footprints4 = self._t_fp4.data_ptr() if hp.footprints4.shape[0] else None
+            self.plan.footprints2 = self._t_fp2.data_ptr() if hp.footprints2.shape[0] else None
 
         table = _lib.GRAVITY_COMPONENTS if physics == "gravity" else _lib.MAGNETIC_COMPONENTS
         code = _lib.PF_GRAVITY if physics == "gravity" else _lib.PF_MAGNETICS

@@ -45,6 +45,12 @@ class TilePlan:
     tile_cell_col: np.ndarray    # (n_tiles, TILE_CELLS) int32, -1 = padding
     tile_n_nodes: np.ndarray     # (n_tiles,) int32
     method: str = ""
+    # tensor meshes only (z-marching kernel, see include/pf_cuda.h)
+    grid_shape: tuple | None = None
+    grid_axes: tuple | None = None        # (xs, ys, zs) float64
+    grid_colmap: np.ndarray | None = None  # (nx*ny*nz,) int32, None = all active
+    footprints4: np.ndarray | None = None  # (n, 6) int32
+    footprints2: np.ndarray | None = None
 
     @property
     def node_evaluations(self) -> int:
@@ -216,8 +222,61 @@ def build_tile_plan_tensor(axis_nodes, active_index=None) -> TilePlan:
     _lib.check(lib.pf_plan_tensor_fill(nx, ny, nz, ptr(xs), ptr(ys), ptr(zs), bx, by, bz, ptr(act),
                                        n_act, ptr(used), n_tiles, ptr(tile_xyz), ptr(tile_cell_nodes),
                                        ptr(tile_cell_col), ptr(tile_n_nodes)), "pf_plan_tensor_fill")
-    return TilePlan(int(n_tiles), int(n_cells), tile_xyz, tile_cell_nodes, tile_cell_col,
-                    tile_n_nodes, "tensor")
+    colmap = None
+    if act is not None:
+        colmap = np.full(nx * ny * nz, -1, dtype=np.int32)
+        colmap[act] = np.arange(act.size, dtype=np.int32)
+    plan = TilePlan(int(n_tiles), int(n_cells), tile_xyz, tile_cell_nodes, tile_cell_col,
+                    tile_n_nodes, "tensor", grid_shape=(nx, ny, nz), grid_axes=(xs, ys, zs),
+                    grid_colmap=colmap)
+    # keep a footprint set only if it evaluates fewer node slots per cell than the bricks
+    brick_slots = float((-(-tile_n_nodes.astype(np.int64) // _ROUND) * _ROUND).sum())
+    for name, ncap in (("footprints4", 1024), ("footprints2", 512)):
+        fps = march_footprints(nx, ny, nz, ncap, act)
+        nodes = (fps[:, 2].astype(np.int64) + 1) * (fps[:, 3] + 1)
+        slots = float(((-(-nodes // _ROUND) * _ROUND) * (fps[:, 5] - fps[:, 4] + 1)).sum())
+        setattr(plan, name, fps if slots < 0.95 * brick_slots else np.zeros((0, 6), np.int32))
+    return plan
+
+
+def march_footprints(nx, ny, nz, ncap, active_index=None):
+    """
+    (x, y) footprints for the z-marching kernel: an a x b grid of rectangles,
+    each with (w + 1)(h + 1) <= ncap nodes per layer, chosen to minimise the
+    number of 256-thread node rounds per layer; rows are
+    (ix0, iy0, w, h, iz_begin, iz_end).
+    """
+    best = None
+    for a in range(1, nx + 1):
+        w = -(-nx // a)
+        if (w + 1) * 2 > ncap:
+            continue
+        for b in range(1, ny + 1):
+            h = -(-ny // b)
+            if (w + 1) * (h + 1) > ncap:
+                continue
+            cost = a * b * (4 * -(-((w + 1) * (h + 1)) // _ROUND) + -(-(w * h) // _ROUND))
+            key = (cost, a)            # fewer x splits = longer contiguous G runs
+            if best is None or key < best[0]:
+                best = (key, (a, b))
+    a, b = best[1]
+    xb = [nx * i // a for i in range(a + 1)]
+    yb = [ny * j // b for j in range(b + 1)]
+    fps = []
+    if active_index is not None:
+        act = np.asarray(active_index, dtype=np.int64)
+        aix, aiy, aiz = act % nx, (act // nx) % ny, act // (nx * ny)
+    for j in range(b):
+        for i in range(a):
+            x0, x1, y0, y1 = xb[i], xb[i + 1], yb[j], yb[j + 1]
+            z0, z1 = 0, nz
+            if active_index is not None:
+                inside = (aix >= x0) & (aix < x1) & (aiy >= y0) & (aiy < y1)
+                if not inside.any():
+                    continue
+                z0, z1 = int(aiz[inside].min()), int(aiz[inside].max()) + 1
+            fps.append((x0, y0, x1 - x0, y1 - y0, z0, z1))
+    return np.asarray(fps, dtype=np.int32).reshape(-1, 6)
 
 
 def tensor_axes_of(mesh):

@@ -100,6 +100,60 @@ def test_adjoint_linearity_and_store_modes(name):
     assert np.array_equal(eng.to_host(eng.forward_dev(x1)), eng.to_host(eng.forward_dev(x1)))
 
 
+MARCH_CASES = [
+    ("gravity", ["gz"], "scalar"),
+    ("gravity", ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"], "scalar"),
+    ("gravity", ["gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "guv"], "scalar"),
+    ("magnetics", ["tmi"], "scalar"),
+    ("magnetics", ["tmi"], "vector"),
+    ("magnetics", ["bx", "by", "bz"], "vector"),
+    ("magnetics", ["tmi", "bx"], "scalar"),
+    ("magnetics", ["tmi_x", "tmi_y", "tmi_z"], "scalar"),
+    ("magnetics", ["bxx", "bxy", "bxz", "byy", "byz", "bzz", "tmi_z"], "vector"),
+]
+
+
+@pytest.mark.parametrize("physics,comps,mt", MARCH_CASES, ids=lambda v: "+".join(v) if isinstance(v, list) else v)
+@pytest.mark.parametrize("masked", [False, True], ids=["all_active", "topography"])
+def test_marching_kernel_vs_tile_kernel_and_oracle(physics, comps, mt, masked):
+    """The z-marching kernel (tensor meshes) against the generic tile kernel and the oracle:
+    G rows and forward_only, all component families, with and without inactive cells."""
+    mesh = TensorMesh([[(4.0, 3, -1.2), (4.0, 34), (4.0, 3, 1.2)], [(5.0, 30)], [(3.0, 12)]], "CCN")
+    active = None
+    if masked:
+        cc = mesh.cell_centers
+        active = np.nonzero(cc[:, 2] < -6.0 + 5.0 * np.exp(-((cc[:, 0] / 40.0) ** 2 + (cc[:, 1] / 50.0) ** 2)))[0]
+    loc = grid_receivers(12, 60.0, 2.0, 3)
+    # generic positions (a receiver ~1e-14 m off a node column makes the reference's own
+    # third-order kernels overflow: -x_i / ((x_k + r) r) with x_k + r == 0) ...
+    loc[:, :2] += np.random.default_rng(5).uniform(-1.0, 1.0, (12, 2))
+    loc[0, :2] = mesh.nodes_x[20], mesh.nodes_y[11]        # ... and one exactly above a node
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh), active)
+    assert plan.footprints4.shape[0] > 0 and plan.footprints2.shape[0] > 0
+    kw = dict(b0=B0, model_type=mt, plan=plan)
+    march = CudaEngine(physics, None, None, [(loc, comps)], use_marching=True, **kw)
+    tile = CudaEngine(physics, None, None, [(loc, comps)], use_marching=False, **kw)
+    assert march.plan.grid_nx == 40 and tile.plan.grid_nx == 0
+    cn = mesh.cell_nodes if active is None else mesh.cell_nodes[active]
+    uniq, inv = np.unique(cn, return_inverse=True)
+    ora = OracleSimulation(physics, mesh.nodes[uniq], inv.reshape(cn.shape), [(loc, comps)], b0=B0, model_type=mt)
+    G_ref = ora.sensitivity_matrix()
+    march.build_G()
+    tile.build_G()
+    Gm, Gt = march.G_to_numpy(), tile.G_to_numpy()
+    assert rowwise_rel(Gm, G_ref).max() <= RTOL_NORMWISE
+    assert rowwise_rel(Gm, Gt).max() <= 1e-12
+    rng = np.random.default_rng(8)
+    m = rng.uniform(-0.5, 0.5, march.nP)
+    fm = march.to_host(march.forward_dev(march.to_device(m)))
+    assert vec_rel(fm, ora.forward(m)) <= RTOL_NORMWISE
+    assert vec_rel(fm, tile.to_host(tile.forward_dev(tile.to_device(m)))) <= 1e-11
+    # float32 storage through the marching kernel
+    m32 = CudaEngine(physics, None, None, [(loc, comps)], sensitivity_dtype=np.float32, **kw)
+    m32.build_G()
+    assert rowwise_rel(m32.G_to_numpy(), G_ref).max() <= 1e-6
+
+
 def test_row_blocks_are_independent():
     """Rows built from a receiver block equal the same rows of the whole build (sharding invariant)."""
     cfg = CONFIGS["cfg4_tmi_vector"]
