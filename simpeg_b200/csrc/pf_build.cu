@@ -397,8 +397,12 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
 // computed once for the two cell slabs that touch it.  Nodes evaluated per
 // cell: (fw+1)(fh+1)/(fw fh) x (nz+1)/nz ~ 1.1-1.2 (bricks: 1.45-1.5).
 // ---------------------------------------------------------------------------
+#ifndef PF_MARCH_MIN_BLOCKS
+#define PF_MARCH_MIN_BLOCKS 3
+#endif
+
 template <int FAM, int PROG, int SINK, typename GT, int NR>
-__global__ void __launch_bounds__(PF_THREADS, (NR <= 2) ? 3 : 2)
+__global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     pf_march_kernel(const __grid_constant__ LaunchParams p)
 {
     constexpr int NCAP = NR * PF_THREADS;   // node slots per layer
