@@ -137,6 +137,21 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
         double Aee = 0, Ann = 0, Auu = 0, Len = 0, Leu = 0, Lnu = 0;
         if (need & NEED_AEE) Aee = pf_safe_atan2(n * u, e * r);
         if (need & NEED_ANN) Ann = pf_safe_atan2(e * u, n * r);
+#ifndef PF_NO_ATAN_IDENTITY
+        if ((need & (NEED_AEE | NEED_ANN | NEED_AUU)) == (NEED_AEE | NEED_ANN | NEED_AUU)) {
+            // The three arguments a = nu/(er), b = eu/(nr), c = en/(ur) share the sign of
+            // e n u and satisfy ab + bc + ca = 1, hence atan a + atan b + atan c = +-pi/2;
+            // with exactly one zero coordinate the sum is +-pi/2 by the sign of the other
+            // two, with two or more it is 0 (safe_atan2 conventions).  Saves one atan.
+            const int he = __double2hiint(e), hn = __double2hiint(n), hu = __double2hiint(u);
+            const int zeros = (int)(((he << 1) | __double2loint(e)) == 0) + (int)(((hn << 1) | __double2loint(n)) == 0)
+                              + (int)(((hu << 1) | __double2loint(u)) == 0);
+            const int sgn = (he ^ hn ^ hu) & 0x80000000;
+            double S = __hiloint2double(0x3ff921fb ^ sgn, 0x54442d18);   // +-pi/2
+            if (zeros >= 2) S = 0.0;
+            Auu = (S - Aee) - Ann;
+        } else
+#endif
         if (need & NEED_AUU) Auu = pf_safe_atan2(e * n, u * r);
         if (need & NEED_LEN) Len = pf_safe_log(u, e, n, r);
         if (need & NEED_LEU) Leu = pf_safe_log(n, e, u, r);
@@ -181,11 +196,12 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
     if (PROG != PROG_GENERIC) {
         // one component "tmi" (magnetics/_numba/_3d_mesh.py:352-372), hoisted to the node
         eval_raw<12>(NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU, e, n, u, k);
-        const double bx = k.v0 * fx + k.v3 * fy + k.v4 * fz;
-        const double by = k.v3 * fx + k.v1 * fy + k.v5 * fz;
-        const double bz = k.v4 * fx + k.v5 * fy + k.v2 * fz;
+        // (explicit FMAs: this combination is hoisted to the node anyway, see the header)
+        const double bx = fma(k.v4, fz, fma(k.v3, fy, k.v0 * fx));
+        const double by = fma(k.v5, fz, fma(k.v1, fy, k.v3 * fx));
+        const double bz = fma(k.v2, fz, fma(k.v5, fy, k.v4 * fx));
         if (PROG == PROG_TMI_SCALAR) {
-            planes[j] = bx * fx + by * fy + bz * fz;
+            planes[j] = fma(bz, fz, fma(by, fy, bx * fx));
         } else {
             planes[j] = bx;
             planes[STRIDE + j] = by;
