@@ -41,7 +41,10 @@ enum { CT_SINGLE = 0, CT_MAG3 = 1, CT_TMI6 = 2 };
 enum { PK_RAW = 0, PK_DOT3 = 1, PK_QUAD = 2 };
 enum { SINK_STORE = 0, SINK_FORWARD = 1, SINK_GTV = 2, SINK_DIAG = 3 };
 // PROG_TMI_*: one component "tmi" (the value is the number of column blocks)
-enum { PROG_GENERIC = 0, PROG_TMI_SCALAR = 1, PROG_TMI_VECTOR = 3 };
+// PROG_ALL6: family 12 with all six primitives needed (descriptor-driven planes, but the node
+// evaluation is branch-free so the compiler interleaves the five transcendentals)
+enum { PROG_GENERIC = 0, PROG_TMI_SCALAR = 1, PROG_TMI_VECTOR = 3, PROG_ALL6 = 6 };
+#define PF_IS_TMI(P) ((P) == PROG_TMI_SCALAR || (P) == PROG_TMI_VECTOR)
 
 constexpr int MAX_PLANES = 10;
 constexpr int MAX_OUT = 32;
@@ -77,6 +80,9 @@ struct LaunchParams {
     int n_fwd;         // components handled by this launch
     int need;          // family-12 primitive mask / family-3 kernel mask
     int nblk;          // 1 (gravity, scalar) or 3 (vector model)
+    int direct;        // outs[o].plane == o for every o (phase 2 can unroll with constant offsets)
+    int raw_mask;      // raw kernels stored as planes: bit q set -> slot = rank of q among the set bits
+    int n_combo;       // planes [n_planes - n_combo, n_planes) are DOT3 / QUAD combinations
     int pad;
     PlaneDesc planes[MAX_PLANES];
     OutDesc outs[MAX_OUT];
@@ -193,7 +199,7 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
 {
     Raw10 k;
     const double fx = p.fx, fy = p.fy, fz = p.fz;
-    if (PROG != PROG_GENERIC) {
+    if (PF_IS_TMI(PROG)) {
         // one component "tmi" (magnetics/_numba/_3d_mesh.py:352-372), hoisted to the node
         eval_raw<12>(NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU, e, n, u, k);
         // (explicit FMAs: this combination is hoisted to the node anyway, see the header)
@@ -210,12 +216,19 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         return;
     }
     eval_raw<FAM>(p.need, e, n, u, k);
-    for (int s = 0; s < p.n_planes; ++s) {
+    // raw planes: straight-line predicated stores (no descriptor loop)
+    {
+        const int rm = p.raw_mask;   // raw planes occupy slots 0.. in increasing q (host guarantees it)
+        double *dst = planes + j;
+#define PF_RAW(q, v) if (rm & (1 << q)) { *dst = (v); dst += STRIDE; }
+        PF_RAW(0, k.v0) PF_RAW(1, k.v1) PF_RAW(2, k.v2) PF_RAW(3, k.v3) PF_RAW(4, k.v4)
+        PF_RAW(5, k.v5) PF_RAW(6, k.v6) PF_RAW(7, k.v7) PF_RAW(8, k.v8) PF_RAW(9, k.v9)
+#undef PF_RAW
+    }
+    for (int s = p.n_planes - p.n_combo; s < p.n_planes; ++s) {   // raw planes come first
         const PlaneDesc &pd = p.planes[s];
         double val;
-        if (pd.kind == PK_RAW) {
-            val = pick(k, pd.q[0]);
-        } else if (pd.kind == PK_DOT3) {
+        if (pd.kind == PK_DOT3) {
             val = pick(k, pd.q[0]) * fx + pick(k, pd.q[1]) * fy + pick(k, pd.q[2]) * fz;
         } else {
             const double kxx = pick(k, pd.q[0]), kyy = pick(k, pd.q[1]), kzz = pick(k, pd.q[2]);
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
     const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
     const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
     const int64_t nC = p.plan.n_cells;
-    const int nblk = (PROG == PROG_GENERIC) ? p.nblk : PROG;
+    const int nblk = PF_IS_TMI(PROG) ? PROG : p.nblk;
 
     // ---- tile-stationary state ------------------------------------------------
     const int nn = p.plan.tile_n_nodes[tile];
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
 
         // ---- phase 2: cells ---------------------------------------------------
         const char *pbase = reinterpret_cast<const char *>(planes);
-        if (PROG != PROG_GENERIC) {
+        if (PF_IS_TMI(PROG)) {
             // single component: row = row_offset + r, factor of the only component
             const int64_t row = p.row_offset + r * p.n_comp_total + p.outs[0].ci;
             const double factor = p.outs[0].factor;
@@ -406,12 +419,18 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
 // z-marching kernel for tensor meshes (SINK_STORE, SINK_FORWARD).
 //
 // One CTA = one (x, y) footprint of the mesh x one chunk of receivers.  For
-// every receiver the CTA sweeps the node layers bottom-up: layer iz+1 is
-// evaluated (phase 1) into one of three rotating shared-memory buffers while
-// the cells between layers iz and iz+1 are combined (phase 2) from the other
-// two -- one __syncthreads per layer, and the node kernels of a layer are
-// computed once for the two cell slabs that touch it.  Nodes evaluated per
-// cell: (fw+1)(fh+1)/(fw fh) x (nz+1)/nz ~ 1.1-1.2 (bricks: 1.45-1.5).
+// every receiver the CTA sweeps the node layers bottom-up.  Per layer L:
+//   phase 1  the output planes of the layer's nodes are evaluated into one of
+//            two alternating shared-memory buffers;
+//   phase 2  every cell column forms the corner difference of the layer,
+//                D_L = k(x0,y0) - k(x1,y0) - k(x0,y1) + k(x1,y1),
+//            and emits the cell between layers L-1 and L as D_L - D_{L-1}
+//            (= -k0+k1+k2-k3+k4-k5-k6+k7 of _numba_utils.py:18-45, associated
+//            layer by layer), keeping D_L in a thread-private shared slot for
+//            the next slab: 4 instead of 8 gathers per cell and output, and a
+//            node layer is evaluated once for the two slabs that touch it.
+// One __syncthreads per layer.  Nodes evaluated per cell:
+// (fw+1)(fh+1)/(fw fh) x (nz+1)/nz ~ 1.1-1.2 (bricks: 1.45-1.5).
 // ---------------------------------------------------------------------------
 #ifndef PF_MARCH_MIN_BLOCKS
 #define PF_MARCH_MIN_BLOCKS 3
@@ -425,8 +444,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     constexpr int LAYER_BYTES = NCAP * 8;
     extern __shared__ double smem[];
     const int n_planes = p.n_planes;
+    const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
     const int buf_doubles = n_planes * NCAP;
-    double *wacc = smem + 3 * (size_t)buf_doubles;  // [WARPS][n_fwd] (forward)
+    double *dprev = smem + 2 * (size_t)buf_doubles;           // [n_out][NR][THREADS] corner differences
+    double *wacc = dprev + (size_t)n_out * NR * PF_THREADS;   // [WARPS][n_fwd] (forward)
+    // per-output bookkeeping, refreshed once per receiver: destination of column 0 of
+    // the output's row/block (store) or of its model block (forward), and its factor
+    __shared__ unsigned long long s_dst[MAX_OUT];
+    __shared__ double s_fac[MAX_OUT];
 
     const int tid = threadIdx.x;
     const int nx = p.plan.grid_nx, ny = p.plan.grid_ny;
@@ -439,9 +464,9 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
     const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
     const int64_t nC = p.plan.n_cells;
-    const int nblk = (PROG == PROG_GENERIC) ? p.nblk : PROG;
     const int64_t layer_stride = (int64_t)nx * ny;
     const int sW = W1 * 8;  // byte stride of one node row inside a layer plane
+    const bool direct = PF_IS_TMI(PROG) || p.direct;
 
     // ---- footprint-stationary state -------------------------------------------
     double x[NR], y[NR];
@@ -471,81 +496,91 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
         const double rx = __ldg(p.receivers + 3 * r);
         const double ry = __ldg(p.receivers + 3 * r + 1);
         const double rz = __ldg(p.receivers + 3 * r + 2);
-
-        // first node layer -> buffer iz_begin % 3
-        {
-            const double u = __ldg(p.plan.grid_zs + iz_begin) - rz;
-            double *first = smem + (iz_begin % 3) * buf_doubles;
-#pragma unroll 1
-            for (int k = 0; k < NR; ++k) {
-                const int j = tid + k * PF_THREADS;
-                const double xx = (k == 0) ? x[0] : ((k == 1) ? x[1 % NR] : ((k == 2) ? x[2 % NR] : x[3 % NR]));
-                const double yy = (k == 0) ? y[0] : ((k == 1) ? y[1 % NR] : ((k == 2) ? y[2 % NR] : y[3 % NR]));
-                if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, first, j);
-            }
+        if (tid < n_out) {
+            const OutDesc &od = p.outs[tid];
+            const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
+            s_dst[tid] = (SINK == SINK_STORE)
+                             ? (unsigned long long)(reinterpret_cast<GT *>(p.G) + row * p.ldG + (int64_t)od.blk * nC)
+                             : (unsigned long long)(p.model + (int64_t)od.blk * nC);
+            s_fac[tid] = od.factor;
         }
-        __syncthreads();
 
-        for (int iz = iz_begin; iz < iz_end; ++iz) {
-            double *upper = smem + ((iz + 1) % 3) * buf_doubles;
-            const double *lower = smem + (iz % 3) * buf_doubles;
-            // ---- phase 1: node layer iz+1 ----------------------------------------
+        // node layers iz_begin .. iz_end; the cells between layers L-1 and L are emitted at L
+        for (int L = iz_begin; L <= iz_end; ++L) {
+            double *planes = smem + (L & 1) * buf_doubles;
+            // ---- phase 1: node layer L ---------------------------------------------
             {
-                const double u = __ldg(p.plan.grid_zs + iz + 1) - rz;
+                const double u = __ldg(p.plan.grid_zs + L) - rz;
 #pragma unroll 1
                 for (int k = 0; k < NR; ++k) {
                     const int j = tid + k * PF_THREADS;
                     const double xx = (k == 0) ? x[0] : ((k == 1) ? x[1 % NR] : ((k == 2) ? x[2 % NR] : x[3 % NR]));
                     const double yy = (k == 0) ? y[0] : ((k == 1) ? y[1 % NR] : ((k == 2) ? y[2 % NR] : y[3 % NR]));
-                    if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, upper, j);
+                    if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, planes, j);
                 }
             }
             __syncthreads();
-            // ---- phase 2: cells between layers iz and iz+1 --------------------------
-            const char *lo = reinterpret_cast<const char *>(lower);
-            const char *up = reinterpret_cast<const char *>(upper);
+            // ---- phase 2: corner differences of layer L; cells of slab L-1 -------------
+            const char *pl = reinterpret_cast<const char *>(planes);
+            const bool emit = L > iz_begin;
             int col[NR];
 #pragma unroll
             for (int s = 0; s < NR; ++s) {
                 col[s] = -1;
-                if (cbase[s] >= 0) {
-                    const int64_t idx = cbase[s] + layer_stride * iz;
+                if (emit && cbase[s] >= 0) {
+                    const int64_t idx = cbase[s] + layer_stride * (L - 1);
                     col[s] = p.plan.grid_colmap ? __ldg(p.plan.grid_colmap + idx) : (int)idx;
                 }
             }
-            const int n_out = (PROG == PROG_GENERIC) ? p.n_out : PROG;
             double fsum = 0.0;
-            for (int o = 0; o < n_out; ++o) {
-                const OutDesc &od = p.outs[o];
-                const int plane = (PROG == PROG_GENERIC) ? od.plane : o;
-                const int blk = (PROG == PROG_GENERIC) ? od.blk : o;
-                const int poff = plane * LAYER_BYTES;
-                const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
-                GT *grow = reinterpret_cast<GT *>(p.G) + row * p.ldG + (int64_t)blk * nC;
+#define PF_PHASE2_BODY(O, POFF)                                                                   \
+            {                                                                                     \
+                GT *grow = reinterpret_cast<GT *>(s_dst[O]);                                      \
+                const double *mrow = reinterpret_cast<const double *>(s_dst[O]);                  \
+                const double factor = s_fac[O];                                                   \
+                double *dp = dprev + (size_t)(O) * (NR * PF_THREADS) + tid;                       \
+                _Pragma("unroll") for (int s = 0; s < NR; ++s) {                                  \
+                    if (cbase[s] < 0) continue;                                                   \
+                    const char *q = pl + (POFF) + o00[s];                                         \
+                    const double d_new = *reinterpret_cast<const double *>(q)                     \
+                                         - *reinterpret_cast<const double *>(q + 8)               \
+                                         - *reinterpret_cast<const double *>(q + sW)              \
+                                         + *reinterpret_cast<const double *>(q + sW + 8);         \
+                    const double d_old = dp[s * PF_THREADS];                                      \
+                    dp[s * PF_THREADS] = d_new;                                                   \
+                    if (col[s] < 0) continue;                                                     \
+                    const double g = factor * (d_new - d_old);                                    \
+                    if (SINK == SINK_STORE) grow[(unsigned)col[s]] = (GT)g;                       \
+                    else fsum += g * __ldg(mrow + (unsigned)col[s]);                              \
+                }                                                                                 \
+            }
+            if (direct) {
+                // output o reads plane o: unrolled with compile-time plane offsets
 #pragma unroll
-                for (int s = 0; s < NR; ++s) {
-                    if (col[s] < 0) continue;
-#define PF_LO(o) (*reinterpret_cast<const double *>(lo + poff + (o)))
-#define PF_UP(o) (*reinterpret_cast<const double *>(up + poff + (o)))
-                    const int a = o00[s];
-                    // _numba_utils.py:18-45: -k0+k1+k2-k3+k4-k5-k6+k7 (k0..k3 lower, k4..k7 upper layer)
-                    const double vs = -PF_LO(a) + PF_LO(a + 8) + PF_LO(a + sW) - PF_LO(a + sW + 8)
-                                      + PF_UP(a) - PF_UP(a + 8) - PF_UP(a + sW) + PF_UP(a + sW + 8);
-#undef PF_LO
-#undef PF_UP
-                    const double g = od.factor * vs;
-                    if (SINK == SINK_STORE) grow[(unsigned)col[s]] = (GT)g;
-                    else fsum += g * __ldg(p.model + col[s] + (int64_t)blk * nC);
+                for (int o = 0; o < MAX_PLANES; ++o) {
+                    if (o >= n_out) break;
+                    PF_PHASE2_BODY(o, o * LAYER_BYTES)
+                    if (SINK == SINK_FORWARD && emit && (PF_IS_TMI(PROG) ? (o == n_out - 1) : p.outs[o].last)) {
+                        fsum = warp_sum(fsum);
+                        const int fi = PF_IS_TMI(PROG) ? 0 : p.outs[o].fi;
+                        if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd + fi] += fsum;
+                        fsum = 0.0;
+                    }
                 }
-                if (SINK == SINK_FORWARD && (PROG != PROG_GENERIC ? (o == n_out - 1) : od.last)) {
-                    fsum = warp_sum(fsum);
-                    const int fi = (PROG == PROG_GENERIC) ? od.fi : 0;
-                    if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd + fi] += fsum;
-                    fsum = 0.0;
+            } else {
+                for (int o = 0; o < n_out; ++o) {
+                    const int poff = p.outs[o].plane * LAYER_BYTES;
+                    PF_PHASE2_BODY(o, poff)
+                    if (SINK == SINK_FORWARD && emit && p.outs[o].last) {
+                        fsum = warp_sum(fsum);
+                        if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd + p.outs[o].fi] += fsum;
+                        fsum = 0.0;
+                    }
                 }
             }
+#undef PF_PHASE2_BODY
         }
-        __syncthreads();   // all warps done with the last slab (buffers and wacc are reused)
+        __syncthreads();   // all warps done with the last layer (buffers, dprev and wacc are reused)
         if (SINK == SINK_FORWARD) {
             if (tid < p.n_fwd) {
                 double t = 0.0;
@@ -828,11 +863,67 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
         if (open) ++n;
     }
     for (int i = 0; i < n; ++i) {
-        const LaunchParams &p = passes[i].p;
+        LaunchParams &p = passes[i].p;
+        {
+            // canonical plane order: raw kernels first (increasing q), then the combinations
+            PlaneDesc sorted[MAX_PLANES];
+            int new_of_old[MAX_PLANES];
+            int m = 0;
+            p.raw_mask = 0;
+            for (int q = 0; q < 10; ++q)
+                for (int sl = 0; sl < p.n_planes; ++sl)
+                    if (p.planes[sl].kind == PK_RAW && p.planes[sl].q[0] == q) {
+                        new_of_old[sl] = m;
+                        sorted[m++] = p.planes[sl];
+                        p.raw_mask |= 1 << q;
+                    }
+            p.n_combo = 0;
+            for (int sl = 0; sl < p.n_planes; ++sl)
+                if (p.planes[sl].kind != PK_RAW) {
+                    new_of_old[sl] = m;
+                    sorted[m++] = p.planes[sl];
+                    p.n_combo++;
+                }
+            for (int sl = 0; sl < p.n_planes; ++sl) p.planes[sl] = sorted[sl];
+            for (int o = 0; o < p.n_out; ++o) p.outs[o].plane = new_of_old[p.outs[o].plane];
+            // one plane per output: order the outputs by plane (phase 2 then reads plane o for
+            // output o with compile-time offsets) if every component's outputs stay contiguous
+            if (p.n_out == p.n_planes) {
+                OutDesc by_plane[MAX_OUT];
+                bool distinct = true;
+                bool seen[MAX_PLANES] = {false};
+                for (int o = 0; o < p.n_out; ++o) {
+                    if (seen[p.outs[o].plane]) distinct = false;
+                    seen[p.outs[o].plane] = true;
+                    by_plane[p.outs[o].plane] = p.outs[o];
+                }
+                bool contiguous = distinct;
+                if (distinct) {
+                    bool closed[PF_MAX_COMPONENTS] = {false};
+                    for (int o = 0; o < p.n_out; ++o) {
+                        const int fi = by_plane[o].fi;
+                        if (closed[fi]) contiguous = false;
+                        if (o + 1 == p.n_out || by_plane[o + 1].fi != fi) closed[fi] = true;
+                    }
+                }
+                if (contiguous) {
+                    for (int o = 0; o < p.n_out; ++o) {
+                        p.outs[o] = by_plane[o];
+                        p.outs[o].last = (o + 1 == p.n_out || by_plane[o + 1].fi != by_plane[o].fi);
+                    }
+                }
+            }
+        }
+        p.direct = 1;
+        for (int o = 0; o < p.n_out; ++o)
+            if (p.outs[o].plane != o) p.direct = 0;
         passes[i].prog = PROG_GENERIC;
         if (passes[i].family == 12 && job->physics == PF_MAGNETICS && p.n_fwd == 1 &&
             job->components[p.outs[0].ci] == PF_TMI)
             passes[i].prog = (p.nblk == 3) ? PROG_TMI_VECTOR : PROG_TMI_SCALAR;
+        else if (passes[i].family == 12 &&
+                 p.need == (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU))
+            passes[i].prog = PROG_ALL6;
     }
     return n;
 }
@@ -876,6 +967,7 @@ int launch_pass(const Pass &pass, cudaStream_t stream)
             return launch_tile_kernel<12, PROG_TMI_VECTOR, SINK, GT>(pass.p, stream);
         if (pass.prog == PROG_TMI_SCALAR)
             return launch_tile_kernel<12, PROG_TMI_SCALAR, SINK, GT>(pass.p, stream);
+        if (pass.prog == PROG_ALL6) return launch_tile_kernel<12, PROG_ALL6, SINK, GT>(pass.p, stream);
         return launch_tile_kernel<12, PROG_GENERIC, SINK, GT>(pass.p, stream);
     }
     return launch_tile_kernel<3, PROG_GENERIC, SINK, GT>(pass.p, stream);
@@ -886,7 +978,8 @@ constexpr size_t MARCH_SMEM_LIMIT = 110 * 1024;  // keeps >= 2 CTAs per SM
 
 size_t march_smem(const LaunchParams &p, int nr, bool forward)
 {
-    return (3 * (size_t)p.n_planes * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0)) * sizeof(double);
+    return ((2 * (size_t)p.n_planes + p.n_out) * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0))
+           * sizeof(double);
 }
 
 // node rounds per layer (4 -> 1024-node footprints, 2 -> 512) or 0 when the pass
@@ -923,6 +1016,8 @@ int launch_march_nr(const Pass &pass, cudaStream_t stream)
             return launch_march_kernel<12, PROG_TMI_VECTOR, SINK, GT, NR>(pass.p, stream);
         if (pass.prog == PROG_TMI_SCALAR)
             return launch_march_kernel<12, PROG_TMI_SCALAR, SINK, GT, NR>(pass.p, stream);
+        if (pass.prog == PROG_ALL6)
+            return launch_march_kernel<12, PROG_ALL6, SINK, GT, NR>(pass.p, stream);
         return launch_march_kernel<12, PROG_GENERIC, SINK, GT, NR>(pass.p, stream);
     }
     return launch_march_kernel<3, PROG_GENERIC, SINK, GT, NR>(pass.p, stream);
