@@ -340,6 +340,41 @@ def run_cuda(args):
     value = pairs_total * K / t_build
     prod_gbs = 2 * g_bytes_total * K / (t_jvec + t_jtvec) / 1e9
 
+    # ---- the other sinks of the path (matrix-free forward / G^T v / diag, weighted column
+    #      norms of the stored G), timed on the device on a receiver subsample ------------
+    extras = {}
+    if rank == 0:
+        from simpeg_b200.engine import CudaEngine
+
+        n_sub = min(256, eng.n_rows // len(wl["components"]))
+        sub = CudaEngine(wl["physics"], None, None, [(wl["locations"][:n_sub], wl["components"])],
+                         b0=np.asarray(survey.source_field.b0) if wl["physics"] == "magnetics" else None,
+                         model_type=wl["model_type"], plan=eng.host_plan)
+        sub_pairs = n_sub * nC
+        ws = sub.to_device(w_host[: sub.n_rows])
+
+        def dev_ms(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            best = np.inf
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            return best
+
+        extras = {
+            "sample": f"{n_sub} receivers x full mesh, device-resident vectors, best of 3",
+            "forward_only_dpred_pairs_s": sub_pairs / dev_ms(lambda: sub.forward_dev(x_dev)) * 1e3,
+            "forward_only_gt_dot_v_pairs_s": sub_pairs / dev_ms(lambda: sub.gt_dot_v_dev(ws)) * 1e3,
+            "forward_only_gtg_diag_pairs_s": sub_pairs / dev_ms(lambda: sub.gtg_diag_dev(ws)) * 1e3,
+            "stored_G_colsumsq_gbs": g_bytes_local / dev_ms(lambda: eng.colsumsq_dev(w_local)) / 1e6,
+        }
+        del sub, ws
+
     # ---- end to end through the public API, host buffers in and out -------------
     del sim, eng, x_dev, w_local, step, timers
     gc.collect()
@@ -397,7 +432,7 @@ def run_cuda(args):
         "products": {"metric": "Jvec+Jtvec GB/s", "jvec_jtvec_gbs": prod_gbs,
                      "frac_of_hbm": prod_gbs / (hbm_peak * world), "G_bytes": g_bytes_total},
         "roofline": {
-            "kernel": "pf_tile_kernel<12, SINK_STORE, double> (G build)", "bound": "fp64",
+            "kernel": "pf_march_kernel<12, PROG_TMI_VECTOR, SINK_STORE, double, 4> (G build)", "bound": "fp64",
             "achieved": build_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
             "frac": build_tflops / (fp64_peak / 1e12), "traffic": None,
             "note": f"algorithmic flop-eq/pair = 339*nN/nC + 64 = {flop_eq_per_pair:.1f} (SURVEY 8(d)); "
@@ -415,7 +450,7 @@ def run_cuda(args):
                 "steps": e2e_steps, "checksum": checksum,
                 "what": "new Simulation3DIntegral(engine='cuda') -> sim.G (tile plan on host, upload, "
                         "build) ; sim.Jvec / sim.Jtvec with numpy vectors in and out"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "other_sinks": extras,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = {k: v for k, v in cpu_baseline(wl).items() if k != "seconds"}

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 2
+#define PF_ABI_VERSION 3
 
 typedef enum {
     PF_OK = 0,
@@ -99,6 +99,17 @@ typedef struct {
     const int32_t *grid_colmap;    /* [nx ny nz] or NULL                        */
     const int32_t *footprints4;    /* [n_footprints4][6]                        */
     const int32_t *footprints2;    /* [n_footprints2][6]                        */
+    /*
+     * Optional global node table (n_nodes == 0: absent): the active nodes and
+     * the (nC, 8) cell -> node table exactly as _get_active_nodes returns them
+     * (base.py:371-399), node coordinates as SoA.  When present, pf_gt_dot_v
+     * works in node space: sum_r v_r k(node - receiver_r) is accumulated once per
+     * unique node and the 8-vertex combination is applied once at the end (the
+     * vertex sum is linear), instead of once per (receiver, cell).
+     */
+    int64_t n_nodes;
+    const double *node_xyz;        /* [3][n_nodes]                              */
+    const int32_t *cell_nodes32;   /* [n_cells][8], F-order vertices            */
 } pf_plan;
 
 /*

@@ -597,6 +597,92 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Node-space G^T v (on-the-fly Jtvec).
+//
+//   (G^T v)[cell, b] = sum_r v_r f sum_{8 vertices} s_vertex t_b(node - receiver_r)
+//                    = sum_{8 vertices} s_vertex N_b[node],
+//   N_b[node] = sum_r (v_r f) t_b(node - receiver_r)
+//
+// because the vertex combination is linear: the kernels are accumulated once
+// per UNIQUE node (nN/nC ~ 1.03 evaluations per pair instead of ~1.5 with
+// tiles), one thread per node, no shared-memory exchange, no barrier; the
+// signed 8-vertex sum (_numba_utils.py:18-45) is applied once at the end.
+// Accumulation over receivers is Kahan-compensated (N_b is ~1e4 x larger than
+// the vertex sums it cancels to).
+// ---------------------------------------------------------------------------
+template <int FAM, int PROG>
+__global__ void __launch_bounds__(PF_THREADS, 3)
+    pf_node_gtv_kernel(const __grid_constant__ LaunchParams p, double *partial /* [chunks][nblk][n_nodes] */)
+{
+    extern __shared__ double vals[];   // [n_planes][THREADS], thread-private columns
+    const int tid = threadIdx.x;
+    const int64_t n_nodes = p.plan.n_nodes;
+    const int64_t j = (int64_t)blockIdx.x * PF_THREADS + tid;
+    const bool valid = j < n_nodes;
+    const int64_t jj = valid ? j : 0;
+    const double x = p.plan.node_xyz[jj];
+    const double y = p.plan.node_xyz[n_nodes + jj];
+    const double z = p.plan.node_xyz[2 * n_nodes + jj];
+    const int nblk = PF_IS_TMI(PROG) ? PROG : p.nblk;
+    const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
+    const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
+    const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
+    double a0 = 0, a1 = 0, a2 = 0, c0 = 0, c1 = 0, c2 = 0;   // Kahan sums per column block
+    for (int64_t r = r_begin; r < r_end; ++r) {
+        const double rx = __ldg(p.receivers + 3 * r);
+        const double ry = __ldg(p.receivers + 3 * r + 1);
+        const double rz = __ldg(p.receivers + 3 * r + 2);
+        eval_node<FAM, PROG, PF_THREADS>(p, x - rx, y - ry, z - rz, vals, tid);
+        for (int o = 0; o < n_out; ++o) {
+            const OutDesc &od = p.outs[o];
+            const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
+            const double coef = __ldg(p.vec + row) * od.factor;
+            const int plane = PF_IS_TMI(PROG) ? o : od.plane;
+            const int blk = PF_IS_TMI(PROG) ? o : od.blk;
+            const double term = coef * vals[plane * PF_THREADS + tid];
+            if (blk == 0) { const double yk = term - c0, t = a0 + yk; c0 = (t - a0) - yk; a0 = t; }
+            else if (blk == 1) { const double yk = term - c1, t = a1 + yk; c1 = (t - a1) - yk; a1 = t; }
+            else { const double yk = term - c2, t = a2 + yk; c2 = (t - a2) - yk; a2 = t; }
+        }
+    }
+    if (valid) {
+        double *out = partial + (int64_t)blockIdx.y * nblk * n_nodes + j;
+        out[0] = a0;
+        if (nblk == 3) {
+            out[n_nodes] = a1;
+            out[2 * n_nodes] = a2;
+        }
+    }
+}
+
+// N[i] = sum_chunks partial[chunk][i]
+__global__ void __launch_bounds__(256) pf_node_reduce_kernel(const double *partial, int64_t n_chunks,
+                                                             int64_t n, double *N)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    for (int64_t c = 0; c < n_chunks; ++c) t += partial[c * n + i];
+    N[i] = t;
+}
+
+// result[cell + b nC] += -N0+N1+N2-N3+N4-N5-N6+N7 over the cell's vertices
+__global__ void __launch_bounds__(256) pf_node_to_cells_kernel(const double *N, int64_t n_nodes,
+                                                               const int32_t *cell_nodes, int64_t nC,
+                                                               int nblk, double *result)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const int4 lo = reinterpret_cast<const int4 *>(cell_nodes)[2 * c];
+    const int4 hi = reinterpret_cast<const int4 *>(cell_nodes)[2 * c + 1];
+    for (int b = 0; b < nblk; ++b) {
+        const double *Nb = N + (int64_t)b * n_nodes;
+        const double vs = -Nb[lo.x] + Nb[lo.y] + Nb[lo.z] - Nb[lo.w] + Nb[hi.x] - Nb[hi.y] - Nb[hi.z] + Nb[hi.w];
+        result[c + (int64_t)b * nC] += vs;
+    }
+}
+
 // fields[row_offset + r*n_comp_total + ci[f]] += sum_tiles partial[tile][r*n_fwd + f]
 struct ReduceFwdParams {
     const double *partial;
@@ -1164,13 +1250,58 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
     PF_CHECK_ARG(vec && out, "null vector or output");
     const int64_t nP = pf_job_columns(plan, job);
     const int64_t chunks = column_chunks(plan, job);
-    if (!workspace || workspace_bytes < chunks * nP * (int64_t)sizeof(double)) {
+    const bool node_space = (SINK == SINK_GTV && plan->n_nodes > 0);
+    if (!workspace || (!node_space && workspace_bytes < chunks * nP * (int64_t)sizeof(double))) {
         pf_set_error("column sink: workspace too small");
         return PF_ERR_WORKSPACE;
     }
     static thread_local Pass passes[MAX_PASSES];
     const int n = make_passes(plan, job, passes, MAX_PASSES);
     PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
+    if (SINK == SINK_GTV && plan->n_nodes > 0) {
+        PF_CHECK_ARG(plan->node_xyz && plan->cell_nodes32, "null node table");
+        const int nblk = n_blocks_of(job);
+        const int64_t nN = plan->n_nodes;
+        const int64_t node_ctas = pf_ceil_div(nN, PF_THREADS);
+        const int rc = choose_rc(node_ctas, job->n_receivers, MAX_COLUMN_CHUNKS);
+        const int64_t nchunks = pf_ceil_div(job->n_receivers, rc);
+        if (workspace_bytes < (nchunks + 1) * nblk * nN * (int64_t)sizeof(double)) {
+            pf_set_error("pf_gt_dot_v: workspace too small");
+            return PF_ERR_WORKSPACE;
+        }
+        double *partial = (double *)workspace;
+        double *N = partial + nchunks * nblk * nN;
+        for (int i = 0; i < n; ++i) {
+            LaunchParams &p = passes[i].p;
+            p.vec = vec;
+            p.rc = rc;
+            const size_t smem = (size_t)p.n_planes * PF_THREADS * sizeof(double);
+            dim3 grid((unsigned)node_ctas, (unsigned)nchunks);
+#define PF_LAUNCH_NODE(F, P)                                                                          \
+            pf_node_gtv_kernel<F, P><<<grid, PF_THREADS, smem, (cudaStream_t)stream>>>(p, partial)
+            if (passes[i].family == 3) PF_LAUNCH_NODE(3, PROG_GENERIC);
+            else if (passes[i].prog == PROG_TMI_VECTOR) PF_LAUNCH_NODE(12, PROG_TMI_VECTOR);
+            else if (passes[i].prog == PROG_TMI_SCALAR) PF_LAUNCH_NODE(12, PROG_TMI_SCALAR);
+            else if (passes[i].prog == PROG_ALL6) PF_LAUNCH_NODE(12, PROG_ALL6);
+            else PF_LAUNCH_NODE(12, PROG_GENERIC);
+#undef PF_LAUNCH_NODE
+            PF_COUNT_LAUNCH();
+            PF_CUDA_OK(cudaGetLastError());
+            const double *src = partial;
+            if (nchunks > 1) {
+                pf_node_reduce_kernel<<<(unsigned)pf_ceil_div(nblk * nN, 256), 256, 0, (cudaStream_t)stream>>>(
+                    partial, nchunks, nblk * nN, N);
+                PF_COUNT_LAUNCH();
+                PF_CUDA_OK(cudaGetLastError());
+                src = N;
+            }
+            pf_node_to_cells_kernel<<<(unsigned)pf_ceil_div(plan->n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
+                src, nN, plan->cell_nodes32, plan->n_cells, nblk, out);
+            PF_COUNT_LAUNCH();
+            PF_CUDA_OK(cudaGetLastError());
+        }
+        return PF_OK;
+    }
     for (int i = 0; i < n; ++i) {
         LaunchParams &p = passes[i].p;
         p.vec = vec;
@@ -1191,7 +1322,14 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
 extern "C" int64_t pf_gt_dot_v_workspace_bytes(const pf_plan *plan, const pf_job *job)
 {
     if (!plan || !job) return -1;
-    return column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
+    int64_t bytes = column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
+    if (plan->n_nodes > 0) {
+        const int rc = choose_rc(pf_ceil_div(plan->n_nodes, PF_THREADS), job->n_receivers, MAX_COLUMN_CHUNKS);
+        const int64_t nchunks = pf_ceil_div(job->n_receivers > 0 ? job->n_receivers : 1, rc);
+        const int64_t node_bytes = (nchunks + 1) * n_blocks_of(job) * plan->n_nodes * (int64_t)sizeof(double);
+        if (node_bytes > bytes) bytes = node_bytes;
+    }
+    return bytes;
 }
 
 extern "C" int pf_gt_dot_v(const pf_plan *plan, const pf_job *job, const double *v, double *result,
@@ -1202,7 +1340,8 @@ extern "C" int pf_gt_dot_v(const pf_plan *plan, const pf_job *job, const double 
 
 extern "C" int64_t pf_gtg_diag_workspace_bytes(const pf_plan *plan, const pf_job *job)
 {
-    return pf_gt_dot_v_workspace_bytes(plan, job);
+    if (!plan || !job) return -1;
+    return column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
 }
 
 extern "C" int pf_gtg_diag(const pf_plan *plan, const pf_job *job, const double *w, double *diag,

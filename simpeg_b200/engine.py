@@ -47,7 +47,7 @@ class CudaEngine:
 
     def __init__(self, physics, nodes, cell_nodes, receiver_list, b0=None,
                  model_type="scalar", sensitivity_dtype=np.float64, device=None,
-                 plan: TilePlan | None = None, use_marching=True):
+                 plan: TilePlan | None = None, use_marching=True, use_node_space=True):
         torch = _require_cuda()
         self.torch = torch
         self.lib = _lib.load_library()
@@ -78,6 +78,7 @@ class CudaEngine:
             n_tiles=hp.n_tiles, n_cells=hp.n_cells, tile_cells=TILE_CELLS, tile_nodes=TILE_NODES,
             tile_xyz=self._t_xyz.data_ptr(), tile_cell_nodes=self._t_cn.data_ptr(),
             tile_cell_col=self._t_col.data_ptr(), tile_n_nodes=self._t_nn.data_ptr())
+        self.use_node_space = bool(use_node_space)
         self.use_marching = bool(use_marching) and hp.grid_shape is not None
         if self.use_marching:
             # tensor mesh: enable the z-marching kernel for G build / forward
@@ -228,8 +229,22 @@ class CudaEngine:
                               ws.numel() * 8, self._stream()), name)
         return result
 
+    def _enable_node_space(self):
+        """Upload the global node table (once) so that pf_gt_dot_v works in node space."""
+        if self.plan.n_nodes or not self.use_node_space or self.nC == 0:
+            return
+        torch = self.torch
+        node_xyz, cn32 = self.host_plan.node_table()
+        with torch.cuda.device(self.device):
+            self._t_node_xyz = torch.from_numpy(node_xyz).to(self.device)
+            self._t_cn32 = torch.from_numpy(cn32).to(self.device)
+        self.plan.n_nodes = node_xyz.shape[1]
+        self.plan.node_xyz = self._t_node_xyz.data_ptr()
+        self.plan.cell_nodes32 = self._t_cn32.data_ptr()
+
     def gt_dot_v_dev(self, v_t, out=None):
         """G_local.T @ v_local without storing G."""
+        self._enable_node_space()
         return self._column_sink(self.lib.pf_gt_dot_v, self.lib.pf_gt_dot_v_workspace_bytes, v_t,
                                  "pf_gt_dot_v", out)
 

@@ -51,6 +51,41 @@ class TilePlan:
     grid_colmap: np.ndarray | None = None  # (nx*ny*nz,) int32, None = all active
     footprints4: np.ndarray | None = None  # (n, 6) int32
     footprints2: np.ndarray | None = None
+    active_index: np.ndarray | None = None  # tensor meshes: mesh indices of the active cells
+    # generic plans keep the (nodes, cell_nodes) they were built from
+    nodes: np.ndarray | None = None
+    cell_nodes: np.ndarray | None = None
+
+    def node_table(self):
+        """
+        (node_xyz (3, nN) float64, cell_nodes (nC, 8) int32): the unique active nodes and the
+        cell -> node table (what ``_get_active_nodes`` returns, base.py:371-399), for the
+        node-space G^T v kernel.
+        """
+        if self.nodes is not None:
+            nodes, cn = self.nodes, self.cell_nodes
+        else:
+            xs, ys, zs = self.grid_axes
+            nx, ny, nz = self.grid_shape
+            cells = np.arange(nx * ny * nz, dtype=np.int64) if self.active_index is None \
+                else np.asarray(self.active_index, dtype=np.int64)
+            ix, iy, iz = cells % nx, (cells // nx) % ny, cells // (nx * ny)
+            n0 = ix + (nx + 1) * (iy + (ny + 1) * iz)
+            sx, sy = 1, nx + 1
+            sz = (nx + 1) * (ny + 1)
+            cn = np.stack([n0, n0 + sx, n0 + sy, n0 + sx + sy,
+                           n0 + sz, n0 + sx + sz, n0 + sy + sz, n0 + sx + sy + sz], axis=1)
+            X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+            nodes = np.stack([X.reshape(-1, order="F"), Y.reshape(-1, order="F"), Z.reshape(-1, order="F")], axis=1)
+        # keep only the nodes that are used (inactive cells)
+        used = np.zeros(nodes.shape[0], dtype=bool)
+        used[np.asarray(cn).ravel()] = True
+        if not used.all():
+            remap = np.cumsum(used) - 1
+            nodes = nodes[used]
+            cn = remap[cn]
+        return (np.ascontiguousarray(np.asarray(nodes, dtype=np.float64).T),
+                np.ascontiguousarray(np.asarray(cn, dtype=np.int32)))
 
     @property
     def node_evaluations(self) -> int:
@@ -228,7 +263,7 @@ def build_tile_plan_tensor(axis_nodes, active_index=None) -> TilePlan:
         colmap[act] = np.arange(act.size, dtype=np.int32)
     plan = TilePlan(int(n_tiles), int(n_cells), tile_xyz, tile_cell_nodes, tile_cell_col,
                     tile_n_nodes, "tensor", grid_shape=(nx, ny, nz), grid_axes=(xs, ys, zs),
-                    grid_colmap=colmap)
+                    grid_colmap=colmap, active_index=act)
     # keep a footprint set only if it evaluates fewer node slots per cell than the bricks
     brick_slots = float((-(-tile_n_nodes.astype(np.int64) // _ROUND) * _ROUND).sum())
     for name, ncap in (("footprints4", 1024), ("footprints2", 512)):
@@ -359,4 +394,4 @@ def build_tile_plan(nodes, cell_nodes, method="auto") -> TilePlan:
     return TilePlan(n_tiles, n_cells, tile_xyz,
                     tile_cell_nodes.reshape(n_tiles, TILE_CELLS, 8),
                     tile_cell_col.reshape(n_tiles, TILE_CELLS),
-                    ncounts.astype(np.int32), used)
+                    ncounts.astype(np.int32), used, nodes=nodes, cell_nodes=cell_nodes)

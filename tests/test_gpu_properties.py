@@ -148,6 +148,15 @@ def test_marching_kernel_vs_tile_kernel_and_oracle(physics, comps, mt, masked):
     fm = march.to_host(march.forward_dev(march.to_device(m)))
     assert vec_rel(fm, ora.forward(m)) <= RTOL_NORMWISE
     assert vec_rel(fm, tile.to_host(tile.forward_dev(tile.to_device(m)))) <= 1e-11
+    # on-the-fly G^T v: node-space kernel (default) vs tile kernel vs oracle
+    v = rng.uniform(size=march.n_rows)
+    gtv_node = march.to_host(march.gt_dot_v_dev(march.to_device(v)))
+    assert march.plan.n_nodes > 0
+    tile_only = CudaEngine(physics, None, None, [(loc, comps)], use_marching=False, use_node_space=False, **kw)
+    gtv_tile = tile_only.to_host(tile_only.gt_dot_v_dev(tile_only.to_device(v)))
+    assert tile_only.plan.n_nodes == 0
+    assert vec_rel(gtv_node, ora.gt_dot_v(v)) <= RTOL_NORMWISE
+    assert vec_rel(gtv_node, gtv_tile) <= 1e-11
     # float32 storage through the marching kernel
     m32 = CudaEngine(physics, None, None, [(loc, comps)], sensitivity_dtype=np.float32, **kw)
     m32.build_G()
