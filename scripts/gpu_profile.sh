@@ -7,7 +7,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 # 2) full capture of the dominant kernels (build, gemv, gemv_t)
-ncu --set full --clock-control none --import-source on -k regex:pf_tile_kernel -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:"pf_march_kernel|pf_tile_kernel|pf_node_gtv_kernel" -c 3 \
     -o gpurun_out/prof_build_${TAG} python scripts/prof_build.py 296 > gpurun_out/prof_build_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'gemv_kernel|column_kernel' -c 2 \
     -o gpurun_out/prof_products_${TAG} python scripts/prof_build.py 296 > gpurun_out/prof_products_${TAG}.log 2>&1

@@ -50,8 +50,11 @@ __device__ __forceinline__ double warp_sum(double v)
 // column slice; per row: KX independent 128-bit loads per thread, a warp
 // shuffle reduction, one shared-memory slot per (warp, row).
 // ---------------------------------------------------------------------------
-constexpr int GEMV_KX = 4;
 constexpr int GEMV_ROWS = 32;
+// 128-bit vectors of x kept per thread: 4 for fp64 G (8 doubles); 2 for fp32 G (8 floats ->
+// 8 doubles after conversion), so that both variants stay near 60 registers / 4 CTAs per SM
+template <typename GT> struct GemvKx { static constexpr int N = 4; };
+template <> struct GemvKx<float> { static constexpr int N = 2; };
 
 template <typename GT, bool ALIGNED>
 __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G, int64_t rows, int64_t cols,
@@ -59,6 +62,7 @@ __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G,
                                                         double *__restrict__ partial /* [chunks][rows] */)
 {
     constexpr int VN = Vec<GT>::N;
+    constexpr int GEMV_KX = GemvKx<GT>::N;
     using VT = typename Vec<GT>::type;
     constexpr int CHUNK = THREADS * VN * GEMV_KX;
     __shared__ double wpart[WARPS][GEMV_ROWS];
@@ -232,8 +236,8 @@ bool aligned_for_vectors(const void *G, int64_t ld)
 
 int64_t gemv_chunks(int64_t cols, int g_dtype)
 {
-    const int vn = (g_dtype == PF_F32) ? 4 : 2;
-    return pf_ceil_div(cols > 0 ? cols : 1, (int64_t)THREADS * vn * GEMV_KX);
+    const int per_thread = (g_dtype == PF_F32) ? 4 * GemvKx<float>::N : 2 * GemvKx<double>::N;
+    return pf_ceil_div(cols > 0 ? cols : 1, (int64_t)THREADS * per_thread);
 }
 
 int64_t col_chunk_width(int g_dtype)
