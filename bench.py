@@ -434,15 +434,22 @@ def run_cuda(args):
         "roofline": {
             "kernel": "pf_march_kernel<12, PROG_TMI_VECTOR, SINK_STORE, double, 4> (G build)", "bound": "fp64",
             "achieved": build_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-            "frac": build_tflops / (fp64_peak / 1e12), "traffic": None,
+            "frac": build_tflops / (fp64_peak / 1e12),
+            # ncu (profiles/r1f_build_products_summary.md): 7.123 GB written + 0.090 GB read for a
+            # 7.104 GB block of G -> DRAM bytes per launch = 1.0154 x the block it writes
+            "traffic": 1.0154 * g_bytes_local,
             "note": f"algorithmic flop-eq/pair = 339*nN/nC + 64 = {flop_eq_per_pair:.1f} (SURVEY 8(d)); "
-                    "peak = DFMA probe measured in this run (pf_probe_fp64_peak); per GPU",
+                    "peak = DFMA probe measured in this run (pf_probe_fp64_peak); per GPU; "
+                    "ncu: FP64 pipe 58-64 % busy (the kernel issues ~260 FP64 instructions per pair)",
         },
         "roofline_products": {
             "kernel": "gemv_kernel<double> + column_kernel<double,0> (Jvec + Jtvec)", "bound": "hbm",
             "achieved": g_bytes_local * 2 * K / (t_jvec + t_jtvec) / 1e9, "peak": hbm_peak,
             "unit": "GB/s", "frac": g_bytes_local * 2 * K / (t_jvec + t_jtvec) / 1e9 / hbm_peak,
-            "traffic": None, "note": f"algorithmic bytes = rows*cols*8 per product, per GPU; peak = {hbm_src}",
+            # ncu: 7.128 GB (gemv) / 7.118 GB (gemv_t) DRAM traffic for a 7.104 GB block
+            "traffic": 1.0034 * g_bytes_local,
+            "note": f"algorithmic bytes = rows*cols*8 per product, per GPU; traffic = DRAM bytes per "
+                    f"launch scaled from the ncu capture; peak = {hbm_src}",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "jvec_jtvec_gbs": e2e_prod_gbs,
