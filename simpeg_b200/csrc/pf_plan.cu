@@ -95,11 +95,11 @@ extern "C" int pf_plan_tensor_fill(int64_t nx, int64_t ny, int64_t nz, const dou
         }
     PF_CHECK_ARG(t == n_tiles, "n_tiles does not match `used`");
 
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(4)
     for (int64_t i = 0; i < n_tiles * (int64_t)PF_TILE_CELLS; ++i) tile_cell_col[i] = -1;
 
     // node coordinates and node counts per tile
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(4)
     for (int64_t tt = 0; tt < n_tiles; ++tt) {
         const int64_t b = brick_of_tile[tt];
         const int64_t tx = b % g.nbx, ty = (b / g.nbx) % g.nby, tz = b / (g.nbx * g.nby);
@@ -123,7 +123,7 @@ extern "C" int pf_plan_tensor_fill(int64_t nx, int64_t ny, int64_t nz, const dou
 
     // cells: slot = position inside the brick (ascending with the G column)
     const int64_t n_cells = active ? n_active : nx * ny * nz;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(4)
     for (int64_t k = 0; k < n_cells; ++k) {
         const int64_t c = active ? active[k] : k;
         const int64_t ix = c % nx, iy = (c / nx) % ny, iz = c / (nx * ny);
