@@ -1,0 +1,88 @@
+"""GPU: edge cases -- empty and tiny inputs, ragged receiver objects, a public-API run on a
+tensor mesh large enough for the z-marching kernel with topography (inactive cells)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import RTOL_NORMWISE, rowwise_rel, vec_rel
+from oracle.oracle import OracleSimulation
+from sim_fixtures import oracle_for
+from simpeg_b200 import maps
+from simpeg_b200.engine import CudaEngine
+from simpeg_b200.meshes import TensorMesh
+from simpeg_b200.potential_fields import gravity, magnetics
+
+pytestmark = pytest.mark.gpu
+
+
+def test_single_cell_single_receiver():
+    mesh = TensorMesh([[(2.0, 1)], [(3.0, 1)], [(4.0, 1)]], "CCN")
+    loc = np.array([[0.3, -0.4, 1.5]])
+    eng = CudaEngine("gravity", mesh.nodes, mesh.cell_nodes, [(loc, ["gz", "gxx"])])
+    ora = OracleSimulation("gravity", mesh.nodes, mesh.cell_nodes, [(loc, ["gz", "gxx"])])
+    eng.build_G()
+    assert rowwise_rel(eng.G_to_numpy(), ora.sensitivity_matrix()).max() <= RTOL_NORMWISE
+    m = np.array([0.7])
+    assert vec_rel(eng.to_host(eng.forward_dev(eng.to_device(m))), ora.forward(m)) <= RTOL_NORMWISE
+
+
+def test_empty_receiver_object_and_ragged_objects():
+    mesh = TensorMesh([[(5.0, 6)], [(5.0, 5)], [(5.0, 4)]], "CCN")
+    rng = np.random.default_rng(2)
+    a = np.c_[rng.uniform(-10, 10, (3, 2)), np.full(3, 2.0)]
+    b = np.c_[rng.uniform(-10, 10, (5, 2)), np.full(5, 3.0)]
+    rlist = [(a, ["gz"]), (np.zeros((0, 3)), ["gxx", "gz"]), (b, ["gzz", "gxy", "gx"])]
+    eng = CudaEngine("gravity", mesh.nodes, mesh.cell_nodes, rlist)
+    ora = OracleSimulation("gravity", mesh.nodes, mesh.cell_nodes, rlist)
+    assert eng.n_rows == 3 + 0 + 15
+    eng.build_G()
+    G = ora.sensitivity_matrix()
+    assert rowwise_rel(eng.G_to_numpy(), G).max() <= RTOL_NORMWISE
+    v = rng.uniform(size=eng.n_rows)
+    assert vec_rel(eng.to_host(eng.gt_dot_v_dev(eng.to_device(v))), G.T @ v) <= RTOL_NORMWISE
+    assert vec_rel(eng.to_host(eng.gtg_diag_dev(eng.to_device(v))), np.einsum("i,ij,ij->j", v, G, G)) <= RTOL_NORMWISE
+
+
+def test_no_receivers_and_no_active_cells():
+    mesh = TensorMesh([[(5.0, 4)], [(5.0, 4)], [(5.0, 4)]], "CCN")
+    eng = CudaEngine("gravity", mesh.nodes, mesh.cell_nodes, [(np.zeros((0, 3)), ["gz"])])
+    assert eng.n_rows == 0
+    eng.build_G()
+    out = eng.to_host(eng.gt_dot_v_dev(eng.to_device(np.zeros(0))))
+    assert out.shape == (64,) and not out.any()
+    # all cells inactive
+    rx = gravity.receivers.Point(np.array([[0.0, 0.0, 1.0]]), components="gz")
+    survey = gravity.survey.Survey(gravity.sources.SourceField([rx]))
+    sim = gravity.Simulation3DIntegral(mesh, survey=survey, rhoMap=maps.IdentityMap(nP=0),
+                                       active_cells=np.zeros(64, dtype=bool), sensitivity_dtype=np.float64)
+    assert sim.nC == 0
+    d = sim.dpred(np.zeros(0))
+    assert d.shape == (1,) and d[0] == 0.0
+
+
+@pytest.mark.parametrize("store", ["ram", "forward_only"])
+def test_public_api_tensor_mesh_with_topography(store):
+    """Simulation3DIntegral on a mesh that takes the marching-kernel path, with active_cells."""
+    mesh = TensorMesh([[(4.0, 30)], [(4.0, 24)], [(3.0, 10)]], "CCN")
+    cc = mesh.cell_centers
+    active = cc[:, 2] < -4.0 + 3.0 * np.exp(-((cc[:, 0] / 30.0) ** 2 + (cc[:, 1] / 25.0) ** 2))
+    rng = np.random.default_rng(4)
+    loc = np.c_[rng.uniform(-50, 50, (10, 2)), np.full(10, 2.0)]
+    rx = magnetics.receivers.Point(loc, components=["tmi"])
+    src = magnetics.sources.UniformBackgroundField([rx], 52000.0, 65.0, 20.0)
+    survey = magnetics.survey.Survey(src)
+    nC = int(active.sum())
+    sim = magnetics.Simulation3DIntegral(mesh, survey=survey, chiMap=maps.IdentityMap(nP=3 * nC),
+                                         model_type="vector", active_cells=active,
+                                         store_sensitivities=store, sensitivity_dtype=np.float64)
+    assert sim._dev.use_marching and sim._dev.plan.grid_colmap
+    ora = oracle_for(sim)
+    G = ora.sensitivity_matrix()
+    chi = rng.uniform(-0.05, 0.05, 3 * nC)
+    v = rng.uniform(size=survey.nD)
+    assert vec_rel(sim.dpred(chi), G @ chi) <= RTOL_NORMWISE
+    assert vec_rel(sim.Jtvec(chi, v), G.T @ v) <= RTOL_NORMWISE
+    w = rng.uniform(0.5, 1.5, size=survey.nD)
+    assert vec_rel(sim.getJtJdiag(chi, W=sp.diags(w)), np.einsum("i,ij,ij->j", w**2, G, G)) <= RTOL_NORMWISE
+    if store == "ram":
+        assert rowwise_rel(sim.G.to_numpy(), G).max() <= RTOL_NORMWISE
