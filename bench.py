@@ -403,8 +403,7 @@ def run_cuda(args):
         d2h = 8 * (nD + nP)
         checksum = float(np.sum(jv)) + float(np.sum(jtv))
         del sim2, plan
-        gc.collect()
-        torch.cuda.empty_cache()
+        gc.collect()          # G goes back to torch's caching allocator (no cudaFree / cudaMalloc per step)
     e2e_value = pairs_total / float(np.mean(e2e_build))
     e2e_prod_gbs = 2 * g_bytes_total / float(np.mean(e2e_prod)) / 1e9
 

@@ -75,6 +75,20 @@ class ReceiverSharding:
     def max_local_rows(self):
         return max(self.rows_of_rank(r).size for r in range(self.world_size))
 
+    def gather_source_index(self):
+        """
+        For the padded all-gather buffer (world_size blocks of ``max_local_rows()`` entries):
+        position of every global row, so that ``full = gathered[index]`` (cached).
+        """
+        if getattr(self, "_gather_index", None) is None:
+            m = self.max_local_rows()
+            index = np.empty(self.nD, dtype=np.int64)
+            for r in range(self.world_size):
+                rows = self.rows_of_rank(r)
+                index[rows] = r * m + np.arange(rows.size)
+            self._gather_index = (m, index)
+        return self._gather_index
+
 
 class Collectives:
     """Thin wrapper over ``torch.distributed`` (a no-op for a single process)."""
@@ -113,13 +127,15 @@ class Collectives:
 
         if self._dist is None:
             return local            # one process owns every row, already in global order
-        full = torch.zeros(sharding.nD, dtype=local.dtype, device=local.device)
-        m = sharding.max_local_rows()
-        padded = torch.zeros(m, dtype=local.dtype, device=local.device)
-        padded[: local.numel()] = local
+        m, index = sharding.gather_source_index()
+        key = (id(sharding), str(local.device))
+        if getattr(self, "_index_cache", None) is None or self._index_cache[0] != key:
+            self._index_cache = (key, torch.from_numpy(index).to(local.device))
+        if local.numel() == m:
+            padded = local.contiguous()
+        else:
+            padded = torch.zeros(m, dtype=local.dtype, device=local.device)
+            padded[: local.numel()] = local
         gathered = torch.empty(m * self.world_size, dtype=local.dtype, device=local.device)
         self._dist.all_gather_into_tensor(gathered, padded, group=self.group)
-        for r in range(self.world_size):
-            rows = sharding.rows_of_rank(r)
-            full[torch.from_numpy(rows).to(local.device)] = gathered[r * m: r * m + rows.size]
-        return full
+        return gathered[self._index_cache[1]]
