@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const int n_planes = p.n_planes;
     const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
     const int buf_doubles = n_planes * NCAP;
-    double *dprev = smem + 2 * (size_t)buf_doubles;           // [n_out][NR][THREADS] corner differences
+    constexpr int N_BUF = 2;
+    double *dprev = smem + N_BUF * (size_t)buf_doubles;       // [n_out][NR][THREADS] corner differences
     double *wacc = dprev + (size_t)n_out * NR * PF_THREADS;   // [WARPS][n_fwd] (forward)
     // per-output bookkeeping, refreshed once per receiver: destination of column 0 of
     // the output's row/block (store) or of its model block (forward), and its factor
@@ -505,22 +506,19 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
             s_fac[tid] = od.factor;
         }
 
-        // node layers iz_begin .. iz_end; the cells between layers L-1 and L are emitted at L
-        for (int L = iz_begin; L <= iz_end; ++L) {
-            double *planes = smem + (L & 1) * buf_doubles;
-            // ---- phase 1: node layer L ---------------------------------------------
-            {
-                const double u = __ldg(p.plan.grid_zs + L) - rz;
+        // ---- phase 1: output planes of node layer L -> planes ---------------------------
+        auto phase1 = [&](int L, double *planes) {
+            const double u = __ldg(p.plan.grid_zs + L) - rz;
 #pragma unroll 1
-                for (int k = 0; k < NR; ++k) {
-                    const int j = tid + k * PF_THREADS;
-                    const double xx = (k == 0) ? x[0] : ((k == 1) ? x[1 % NR] : ((k == 2) ? x[2 % NR] : x[3 % NR]));
-                    const double yy = (k == 0) ? y[0] : ((k == 1) ? y[1 % NR] : ((k == 2) ? y[2 % NR] : y[3 % NR]));
-                    if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, planes, j);
-                }
+            for (int k = 0; k < NR; ++k) {
+                const int j = tid + k * PF_THREADS;
+                const double xx = (k == 0) ? x[0] : ((k == 1) ? x[1 % NR] : ((k == 2) ? x[2 % NR] : x[3 % NR]));
+                const double yy = (k == 0) ? y[0] : ((k == 1) ? y[1 % NR] : ((k == 2) ? y[2 % NR] : y[3 % NR]));
+                if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, planes, j);
             }
-            __syncthreads();
-            // ---- phase 2: corner differences of layer L; cells of slab L-1 -------------
+        };
+        // ---- phase 2: corner differences of layer L; emits the cells between L-1 and L ----
+        auto phase2 = [&](int L, const double *planes) {
             const char *pl = reinterpret_cast<const char *>(planes);
             const bool emit = L > iz_begin;
             int col[NR];
@@ -579,6 +577,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 }
             }
 #undef PF_PHASE2_BODY
+        };
+
+        // node layers iz_begin .. iz_end; the cells between layers L-1 and L are emitted at L
+        for (int L = iz_begin; L <= iz_end; ++L) {
+            double *planes = smem + (L & 1) * buf_doubles;
+            phase1(L, planes);
+            __syncthreads();
+            phase2(L, planes);
         }
         __syncthreads();   // all warps done with the last layer (buffers, dprev and wacc are reused)
         if (SINK == SINK_FORWARD) {
@@ -1064,7 +1070,8 @@ constexpr size_t MARCH_SMEM_LIMIT = 110 * 1024;  // keeps >= 2 CTAs per SM
 
 size_t march_smem(const LaunchParams &p, int nr, bool forward)
 {
-    return ((2 * (size_t)p.n_planes + p.n_out) * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0))
+    const size_t n_buf = 2;
+    return ((n_buf * (size_t)p.n_planes + p.n_out) * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0))
            * sizeof(double);
 }
 
