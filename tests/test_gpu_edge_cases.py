@@ -86,3 +86,38 @@ def test_public_api_tensor_mesh_with_topography(store):
     assert vec_rel(sim.getJtJdiag(chi, W=sp.diags(w)), np.einsum("i,ij,ij->j", w**2, G, G)) <= RTOL_NORMWISE
     if store == "ram":
         assert rowwise_rel(sim.G.to_numpy(), G).max() <= RTOL_NORMWISE
+
+
+@pytest.mark.parametrize("physics,comps,mt", [
+    ("gravity", ["gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "guv"], "scalar"),
+    ("magnetics", ["tmi", "bx", "by", "bz"], "vector"),
+    ("magnetics", ["tmi_x", "tmi_y", "tmi_z", "bxx", "byz"], "scalar"),
+])
+def test_receivers_inside_below_and_beside_the_mesh(physics, comps, mt):
+    """Borehole-style geometry: nodes on every side of the receivers (all sign combinations of
+    e, n, u, including zeros: receivers in node planes, on cell faces and on mesh edges' lines)."""
+    mesh = TensorMesh([[(3.0, 14)], [(4.0, 12)], [(2.5, 12)]], "CCN")
+    rng = np.random.default_rng(12)
+    inside = np.c_[rng.uniform(-15, 15, (6, 2)), rng.uniform(-25, -5, 6)]      # inside cells (generic)
+    below = np.c_[rng.uniform(-30, 30, (3, 2)), np.full(3, -45.0)]             # below the mesh
+    beside = np.array([[40.0, 3.3, -12.2], [-3.1, -39.0, -7.7]])               # outside, at depth
+    on_planes = np.array([[mesh.nodes_x[5], 1.234, 3.0],                        # e == 0 for a node plane
+                          [0.77, mesh.nodes_y[4], 2.0],                         # n == 0
+                          [mesh.nodes_x[9], mesh.nodes_y[7], 4.0],              # e == n == 0 (above a node)
+                          [50.0, 2.2, mesh.nodes_z[6]]])                        # u == 0, outside the mesh
+    loc = np.vstack([inside, below, beside, on_planes])
+    b0 = np.array([1.2e4, -2.1e4, -4.4e4])
+    from simpeg_b200.tiling import build_tile_plan_tensor, tensor_axes_of
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh))
+    ora = OracleSimulation(physics, mesh.nodes, mesh.cell_nodes, [(loc, comps)], b0=b0, model_type=mt)
+    G = ora.sensitivity_matrix()
+    assert np.isfinite(G).all()
+    for march in (True, False):
+        eng = CudaEngine(physics, None, None, [(loc, comps)], b0=b0, model_type=mt, plan=plan,
+                         use_marching=march, use_node_space=march)
+        eng.build_G()
+        assert rowwise_rel(eng.G_to_numpy(), G).max() <= RTOL_NORMWISE
+        m = rng.uniform(-0.5, 0.5, eng.nP)
+        v = rng.uniform(size=eng.n_rows)
+        assert vec_rel(eng.to_host(eng.forward_dev(eng.to_device(m))), G @ m) <= RTOL_NORMWISE
+        assert vec_rel(eng.to_host(eng.gt_dot_v_dev(eng.to_device(v))), G.T @ v) <= RTOL_NORMWISE
