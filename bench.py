@@ -87,12 +87,13 @@ def make_simulation(wl, survey, comm=None):
     from simpeg_b200.potential_fields import gravity, magnetics
 
     nC = wl["mesh"].n_cells
+    dtype = np.float32 if wl.get("g_dtype") == "f32" else np.float64
     if wl["physics"] == "gravity":
         return gravity.Simulation3DIntegral(wl["mesh"], survey=survey, rhoMap=maps.IdentityMap(nP=nC),
-                                            sensitivity_dtype=np.float64, comm=comm)
+                                            sensitivity_dtype=dtype, comm=comm)
     nP = nC * (3 if wl["model_type"] == "vector" else 1)
     return magnetics.Simulation3DIntegral(wl["mesh"], survey=survey, chiMap=maps.IdentityMap(nP=nP),
-                                          model_type=wl["model_type"], sensitivity_dtype=np.float64,
+                                          model_type=wl["model_type"], sensitivity_dtype=dtype,
                                           comm=comm)
 
 
@@ -270,6 +271,8 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     coll = Collectives()
     wl = make_workload(args.workload, world, args.receivers_per_gpu)
+    wl["g_dtype"] = args.g_dtype
+    g_item = 4 if args.g_dtype == "f32" else 8
     nC = wl["mesh"].n_cells
     rng = np.random.default_rng(5)
     survey = make_survey(wl, wl["locations"])
@@ -295,8 +298,8 @@ def run_cuda(args):
     eng = sim._dev
     pairs_local = eng.n_rows // len(wl["components"]) * nC
     pairs_total = wl["n_rx"] * nC
-    g_bytes_local = eng.n_rows * nP * 8
-    g_bytes_total = nD * nP * 8
+    g_bytes_local = eng.n_rows * nP * g_item
+    g_bytes_total = nD * nP * g_item
 
     x_dev = eng.to_device(v_host)
     w_local = sim._local_rows_of(w_host)
@@ -426,6 +429,7 @@ def run_cuda(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "g_storage": args.g_dtype,
         "config": workload_config(wl, world),
         "ms_build": 1e3 * t_build / K, "ms_jvec": 1e3 * t_jvec / K, "ms_jtvec": 1e3 * t_jtvec / K,
         "products": {"metric": "Jvec+Jtvec GB/s", "jvec_jtvec_gbs": prod_gbs,
@@ -475,6 +479,8 @@ def main():
     ap.add_argument("--receivers-per-gpu", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--g-dtype", default="f64", choices=["f64", "f32"],
+                    help="storage type of G (sensitivity_dtype); BASELINE.json asks for fp64")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -20,11 +20,16 @@ template <> struct Vec<double> {
     static constexpr int N = 2;
     using type = double2;
     __device__ static void unpack(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+    __device__ static void unpack_native(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
 };
 template <> struct Vec<float> {
     static constexpr int N = 4;
     using type = float4;
     __device__ static void unpack(const float4 &v, double *o)
+    {
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    __device__ static void unpack_native(const float4 &v, float *o)
     {
         o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
     }
@@ -153,15 +158,16 @@ __global__ void __launch_bounds__(THREADS) column_kernel(const GT *__restrict__ 
 #pragma unroll
         for (int v = 0; v < VN; ++v) acc[k][v] = 0.0;
 
-    auto load_row = [&](const GT *row, double (&g)[COL_KC][VN]) {
+    // rows are kept in the storage type until they are used (fp32 rows: half the registers)
+    auto load_row = [&](const GT *row, GT (&g)[COL_KC][VN]) {
 #pragma unroll
         for (int k = 0; k < COL_KC; ++k) {
             const int64_t c = c0 + ((int64_t)k * THREADS + tid) * VN;
             if (ALIGNED && c + VN <= cols) {
-                Vec<GT>::unpack(ld_stream(reinterpret_cast<const VT *>(row + c)), g[k]);
+                Vec<GT>::unpack_native(ld_stream(reinterpret_cast<const VT *>(row + c)), g[k]);
             } else {
 #pragma unroll
-                for (int v = 0; v < VN; ++v) g[k][v] = (c + v < cols) ? (double)row[c + v] : 0.0;
+                for (int v = 0; v < VN; ++v) g[k][v] = (c + v < cols) ? row[c + v] : (GT)0;
             }
         }
     };
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(THREADS) column_kernel(const GT *__restrict__ 
     if (MODE == 2) {
         const int64_t nloc = rows;
         for (int64_t i = r0; i < r1; ++i) {
-            double gx[COL_KC][VN], gy[COL_KC][VN], gz[COL_KC][VN];
+            GT gx[COL_KC][VN], gy[COL_KC][VN], gz[COL_KC][VN];
             load_row(G + (3 * i) * ld, gx);
             load_row(G + (3 * i + 1) * ld, gy);
             load_row(G + (3 * i + 2) * ld, gz);
@@ -180,14 +186,14 @@ __global__ void __launch_bounds__(THREADS) column_kernel(const GT *__restrict__ 
 #pragma unroll
                 for (int v = 0; v < VN; ++v) {
                     // magnetics/simulation.py:449-456
-                    const double rowv = ax * gx[k][v] + ay * gy[k][v] + az * gz[k][v];
+                    const double rowv = ax * (double)gx[k][v] + ay * (double)gy[k][v] + az * (double)gz[k][v];
                     acc[k][v] += w * (rowv * rowv);
                 }
         }
     } else {
         int64_t i = r0;
         for (; i + COL_UNROLL <= r1; i += COL_UNROLL) {
-            double g[COL_UNROLL][COL_KC][VN];
+            GT g[COL_UNROLL][COL_KC][VN];
             double yy[COL_UNROLL];
 #pragma unroll
             for (int u = 0; u < COL_UNROLL; ++u) {
@@ -200,20 +206,22 @@ __global__ void __launch_bounds__(THREADS) column_kernel(const GT *__restrict__ 
                 for (int k = 0; k < COL_KC; ++k)
 #pragma unroll
                     for (int v = 0; v < VN; ++v) {
-                        if (MODE == 0) acc[k][v] = fma(yy[u], g[u][k][v], acc[k][v]);
-                        else acc[k][v] = fma(yy[u], g[u][k][v] * g[u][k][v], acc[k][v]);
+                        const double gv = (double)g[u][k][v];
+                        if (MODE == 0) acc[k][v] = fma(yy[u], gv, acc[k][v]);
+                        else acc[k][v] = fma(yy[u], gv * gv, acc[k][v]);
                     }
         }
         for (; i < r1; ++i) {
-            double g[COL_KC][VN];
+            GT g[COL_KC][VN];
             load_row(G + i * ld, g);
             const double yy = __ldg(yv + i);
 #pragma unroll
             for (int k = 0; k < COL_KC; ++k)
 #pragma unroll
                 for (int v = 0; v < VN; ++v) {
-                    if (MODE == 0) acc[k][v] = fma(yy, g[k][v], acc[k][v]);
-                    else acc[k][v] = fma(yy, g[k][v] * g[k][v], acc[k][v]);
+                    const double gv = (double)g[k][v];
+                    if (MODE == 0) acc[k][v] = fma(yy, gv, acc[k][v]);
+                    else acc[k][v] = fma(yy, gv * gv, acc[k][v]);
                 }
         }
     }
