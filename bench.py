@@ -400,9 +400,10 @@ def run_cuda(args):
             e2e_build.append(max_over_ranks(t1 - t0))
             e2e_prod.append(max_over_ranks(t2 - t1))
         plan = sim2._dev.host_plan
-        h2d = (plan.tile_xyz.nbytes + plan.tile_cell_nodes.nbytes + plan.tile_cell_col.nbytes
-               + plan.tile_n_nodes.nbytes + sim2._sharding.local_rows.size // len(wl["components"]) * 24
-               + 8 * (nP + nD))
+        plan_arrays = [plan.tile_xyz, plan.tile_cell_nodes, plan.tile_cell_col, plan.tile_n_nodes,
+                       plan.grid_colmap, plan.footprints4, plan.footprints2] + list(plan.grid_axes or [])
+        h2d = (sum(a.nbytes for a in plan_arrays if a is not None)
+               + sim2._sharding.local_rows.size // len(wl["components"]) * 24 + 8 * (nP + nD))
         d2h = 8 * (nD + nP)
         checksum = float(np.sum(jv)) + float(np.sum(jtv))
         del sim2, plan

@@ -136,6 +136,11 @@ const char *pf_last_error(void);
 /* number of CUDA kernels this library has launched in this process so far */
 int64_t pf_launch_count(void);
 
+/* 1 if every pass of the job runs on the z-marching kernel (tensor-mesh description present
+ * and the output planes fit), so that the tile arrays of the plan are not needed for
+ * pf_build_G (forward == 0) / pf_forward (forward != 0); 0 otherwise. */
+int pf_job_uses_marching(const pf_plan *plan, const pf_job *job, int forward);
+
 /* number of columns of G for a job: nC (gravity, scalar) or 3 nC (vector) */
 int64_t pf_job_columns(const pf_plan *plan, const pf_job *job);
 

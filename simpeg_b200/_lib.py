@@ -34,7 +34,7 @@ MAGNETIC_COMPONENTS = {
 
 # every symbol declared in include/pf_cuda.h
 EXPORTED_SYMBOLS = (
-    "pf_abi_version", "pf_last_error", "pf_launch_count", "pf_job_columns",
+    "pf_abi_version", "pf_last_error", "pf_launch_count", "pf_job_uses_marching", "pf_job_columns",
     "pf_build_G",
     "pf_forward_workspace_bytes", "pf_forward",
     "pf_gt_dot_v_workspace_bytes", "pf_gt_dot_v",
@@ -103,6 +103,7 @@ def load_library() -> ctypes.CDLL:
         "pf_abi_version": (i32, []),
         "pf_last_error": (ctypes.c_char_p, []),
         "pf_launch_count": (i64, []),
+        "pf_job_uses_marching": (i32, [PP, JP, i32]),
         "pf_job_columns": (i64, [PP, JP]),
         "pf_build_G": (i32, [PP, JP, vp, i64, i32, vp]),
         "pf_forward_workspace_bytes": (i64, [PP, JP]),

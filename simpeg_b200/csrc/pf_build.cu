@@ -799,7 +799,8 @@ int need_of_quantity(int family, int q)
 int validate(const pf_plan *plan, const pf_job *job)
 {
     PF_CHECK_ARG(plan && job, "null plan or job");
-    PF_CHECK_ARG(plan->tile_cells == PF_TILE_CELLS && plan->tile_nodes == PF_TILE_NODES,
+    PF_CHECK_ARG(plan->n_tiles == 0 ||
+                     (plan->tile_cells == PF_TILE_CELLS && plan->tile_nodes == PF_TILE_NODES),
                  "tile geometry does not match the library (512 cells / 768 nodes)");
     PF_CHECK_ARG(plan->n_tiles >= 0 && plan->n_cells >= 0, "negative sizes");
     PF_CHECK_ARG(plan->n_tiles == 0 ||
@@ -1146,13 +1147,25 @@ extern "C" int64_t pf_job_columns(const pf_plan *plan, const pf_job *job)
     return plan->n_cells * n_blocks_of(job);
 }
 
+extern "C" int pf_job_uses_marching(const pf_plan *plan, const pf_job *job, int forward)
+{
+    if (validate(plan, job) != PF_OK) return 0;
+    if (plan->grid_nx <= 0) return 0;
+    static thread_local Pass passes[MAX_PASSES];
+    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    if (n <= 0) return 0;
+    for (int i = 0; i < n; ++i)
+        if (!march_rounds(plan, passes[i].p, forward != 0)) return 0;
+    return 1;
+}
+
 extern "C" int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64_t ldG,
                           int g_dtype, void *stream)
 {
     int st = validate(plan, job);
     if (st != PF_OK) return st;
     PF_CHECK_ARG(g_dtype == PF_F64 || g_dtype == PF_F32, "bad g_dtype");
-    if (plan->n_tiles == 0 || job->n_receivers == 0) return PF_OK;
+    if (plan->n_cells == 0 || job->n_receivers == 0) return PF_OK;
     PF_CHECK_ARG(G != nullptr, "null G");
     PF_CHECK_ARG(ldG >= pf_job_columns(plan, job), "ldG smaller than the number of columns");
     st = validate_grid(plan);
@@ -1171,6 +1184,7 @@ extern "C" int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64
             st = (g_dtype == PF_F64) ? launch_march<SINK_STORE, double>(passes[i], nr, (cudaStream_t)stream)
                                      : launch_march<SINK_STORE, float>(passes[i], nr, (cudaStream_t)stream);
         } else {
+            PF_CHECK_ARG(plan->n_tiles > 0, "tile arrays are required for this component set (no marching path)");
             p.rc = choose_rc(plan->n_tiles, job->n_receivers, 65535);
             st = (g_dtype == PF_F64) ? launch_pass<SINK_STORE, double>(passes[i], (cudaStream_t)stream)
                                      : launch_pass<SINK_STORE, float>(passes[i], (cudaStream_t)stream);
@@ -1194,7 +1208,7 @@ extern "C" int pf_forward(const pf_plan *plan, const pf_job *job, const double *
 {
     int st = validate(plan, job);
     if (st != PF_OK) return st;
-    if (plan->n_tiles == 0 || job->n_receivers == 0) return PF_OK;
+    if (plan->n_cells == 0 || job->n_receivers == 0) return PF_OK;
     PF_CHECK_ARG(model && fields, "null model or fields");
     st = validate_grid(plan);
     if (st != PF_OK) return st;
@@ -1216,6 +1230,7 @@ extern "C" int pf_forward(const pf_plan *plan, const pf_job *job, const double *
             p.rc = choose_rc(n_parts, job->n_receivers, 65535);
             st = launch_march<SINK_FORWARD, double>(passes[i], nr, (cudaStream_t)stream);
         } else {
+            PF_CHECK_ARG(plan->n_tiles > 0, "tile arrays are required for this component set (no marching path)");
             p.rc = choose_rc(plan->n_tiles, job->n_receivers, 65535);
             st = launch_pass<SINK_FORWARD, double>(passes[i], (cudaStream_t)stream);
         }
@@ -1253,7 +1268,7 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
 {
     int st = validate(plan, job);
     if (st != PF_OK) return st;
-    if (plan->n_tiles == 0 || job->n_receivers == 0) return PF_OK;
+    if (plan->n_cells == 0 || job->n_receivers == 0) return PF_OK;
     PF_CHECK_ARG(vec && out, "null vector or output");
     const int64_t nP = pf_job_columns(plan, job);
     const int64_t chunks = column_chunks(plan, job);
@@ -1309,6 +1324,7 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
         }
         return PF_OK;
     }
+    PF_CHECK_ARG(plan->n_tiles > 0, "tile arrays are required for this sink");
     for (int i = 0; i < n; ++i) {
         LaunchParams &p = passes[i].p;
         p.vec = vec;

@@ -68,16 +68,9 @@ class CudaEngine:
         self.nC = hp.n_cells
         self.nblk = 1 if (physics == "gravity" or self.scalar) else 3
         self.nP = self.nC * self.nblk
-        with torch.cuda.device(self.device):
-            self._t_xyz = torch.from_numpy(hp.tile_xyz).to(self.device)
-            # torch has no uint16 arithmetic; the bytes are only ever read by the kernel
-            self._t_cn = torch.from_numpy(hp.tile_cell_nodes.view(np.int16)).to(self.device)
-            self._t_col = torch.from_numpy(hp.tile_cell_col).to(self.device)
-            self._t_nn = torch.from_numpy(hp.tile_n_nodes).to(self.device)
-        self.plan = _lib.PfPlan(
-            n_tiles=hp.n_tiles, n_cells=hp.n_cells, tile_cells=TILE_CELLS, tile_nodes=TILE_NODES,
-            tile_xyz=self._t_xyz.data_ptr(), tile_cell_nodes=self._t_cn.data_ptr(),
-            tile_cell_col=self._t_col.data_ptr(), tile_n_nodes=self._t_nn.data_ptr())
+        self.plan = _lib.PfPlan(n_tiles=0, n_cells=hp.n_cells, tile_cells=TILE_CELLS, tile_nodes=TILE_NODES)
+        if hp.has_tiles:
+            self._upload_tiles()
         self.use_node_space = bool(use_node_space)
         self.use_marching = bool(use_marching) and hp.grid_shape is not None
         if self.use_marching:
@@ -131,6 +124,35 @@ class CudaEngine:
         self.G = None
         self.ld = 0
         self._ws = None
+
+    def _upload_tiles(self):
+        """Brick / RCB tile arrays -> device (built lazily for tensor meshes: the z-marching
+        kernel does not need them)."""
+        if self.plan.n_tiles:
+            return
+        torch = self.torch
+        hp = self.host_plan.ensure_tiles()
+        if hp.n_tiles == 0:
+            return
+        with torch.cuda.device(self.device):
+            self._t_xyz = torch.from_numpy(hp.tile_xyz).to(self.device)
+            # torch has no uint16 arithmetic; the bytes are only ever read by the kernel
+            self._t_cn = torch.from_numpy(hp.tile_cell_nodes.view(np.int16)).to(self.device)
+            self._t_col = torch.from_numpy(hp.tile_cell_col).to(self.device)
+            self._t_nn = torch.from_numpy(hp.tile_n_nodes).to(self.device)
+        self.plan.n_tiles = hp.n_tiles
+        self.plan.tile_xyz = self._t_xyz.data_ptr()
+        self.plan.tile_cell_nodes = self._t_cn.data_ptr()
+        self.plan.tile_cell_col = self._t_col.data_ptr()
+        self.plan.tile_n_nodes = self._t_nn.data_ptr()
+
+    def _need_tiles_unless_marching(self, forward):
+        if self.plan.n_tiles:
+            return
+        for job in self.jobs:
+            if not self.lib.pf_job_uses_marching(*self._jp(job), int(forward)):
+                self._upload_tiles()
+                return
 
     # ------------------------------------------------------------------ utils
     def _stream(self):
@@ -194,9 +216,19 @@ class CudaEngine:
     def build_G(self):
         """Fill the local block of G on the device (rows_local x nP, row-major)."""
         torch = self.torch
+        self._need_tiles_unless_marching(False)
         self.ld = -(-max(self.nP, 1) // _G_ALIGN) * _G_ALIGN
         with torch.cuda.device(self.device):
             if self.G is None:
+                need = self.n_rows * self.ld * (8 if self.g_dtype is np.float64 else 4)
+                free, total = torch.cuda.mem_get_info(self.device)
+                reusable = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+                if need > free + reusable:
+                    raise RuntimeError(
+                        f"the local block of G needs {need / 1e9:.1f} GB but only "
+                        f"{(free + reusable) / 1e9:.1f} GB of the {total / 1e9:.0f} GB of this GPU are free: "
+                        "shard the receivers over more GPUs (torchrun), use sensitivity_dtype=np.float32 "
+                        "or store_sensitivities='forward_only'")
                 self.G = torch.empty((self.n_rows, self.ld), dtype=self._g_torch, device=self.device)
             for job in self.jobs:
                 _lib.check(self.lib.pf_build_G(*self._jp(job), self.G.data_ptr(), self.ld,
@@ -206,6 +238,7 @@ class CudaEngine:
     def forward_dev(self, model_t, out=None):
         """fields = G_local @ model without storing G (device tensors)."""
         torch = self.torch
+        self._need_tiles_unless_marching(True)
         with torch.cuda.device(self.device):
             fields = torch.zeros(self.n_rows, dtype=torch.float64, device=self.device) if out is None \
                 else out.zero_()
@@ -245,11 +278,14 @@ class CudaEngine:
     def gt_dot_v_dev(self, v_t, out=None):
         """G_local.T @ v_local without storing G."""
         self._enable_node_space()
+        if not self.plan.n_nodes:
+            self._upload_tiles()
         return self._column_sink(self.lib.pf_gt_dot_v, self.lib.pf_gt_dot_v_workspace_bytes, v_t,
                                  "pf_gt_dot_v", out)
 
     def gtg_diag_dev(self, w_t, out=None):
         """sum_rows w[row] G_local[row, :]**2 without storing G."""
+        self._upload_tiles()
         return self._column_sink(self.lib.pf_gtg_diag, self.lib.pf_gtg_diag_workspace_bytes, w_t,
                                  "pf_gtg_diag", out)
 

@@ -320,7 +320,7 @@ class BasePFSimulation:
         axes = tensor_axes_of(self.mesh)
         if axes is not None:
             active = None if self.nC == self.mesh.n_cells else np.nonzero(self.active_cells)[0]
-            return build_tile_plan_tensor(axes, active)
+            return build_tile_plan_tensor(axes, active, with_tiles=False)
         return build_tile_plan(*self._get_active_nodes())
 
     def _get_components_and_receivers(self):

@@ -86,6 +86,8 @@ class ReceiverSharding:
             for r in range(self.world_size):
                 rows = self.rows_of_rank(r)
                 index[rows] = r * m + np.arange(rows.size)
+            if np.array_equal(index, np.arange(self.nD)):
+                index = None       # equal contiguous blocks: the gathered buffer IS the full vector
             self._gather_index = (m, index)
         return self._gather_index
 
@@ -129,7 +131,7 @@ class Collectives:
             return local            # one process owns every row, already in global order
         m, index = sharding.gather_source_index()
         key = (id(sharding), str(local.device))
-        if getattr(self, "_index_cache", None) is None or self._index_cache[0] != key:
+        if index is not None and (getattr(self, "_index_cache", None) is None or self._index_cache[0] != key):
             self._index_cache = (key, torch.from_numpy(index).to(local.device))
         if local.numel() == m:
             padded = local.contiguous()
@@ -138,4 +140,4 @@ class Collectives:
             padded[: local.numel()] = local
         gathered = torch.empty(m * self.world_size, dtype=local.dtype, device=local.device)
         self._dist.all_gather_into_tensor(gathered, padded, group=self.group)
-        return gathered[self._index_cache[1]]
+        return gathered if index is None else gathered[self._index_cache[1]]

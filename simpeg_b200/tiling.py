@@ -56,6 +56,18 @@ class TilePlan:
     nodes: np.ndarray | None = None
     cell_nodes: np.ndarray | None = None
 
+    def ensure_tiles(self):
+        """Build the brick tile arrays of a tensor plan created with ``with_tiles=False``."""
+        if self.tile_xyz is None:
+            xs, ys, zs = self.grid_axes
+            (self.n_tiles, self.tile_xyz, self.tile_cell_nodes, self.tile_cell_col,
+             self.tile_n_nodes) = _tensor_tiles(xs, ys, zs, self.active_index)
+        return self
+
+    @property
+    def has_tiles(self):
+        return self.tile_xyz is not None
+
     def node_table(self):
         """
         (node_xyz (3, nN) float64, cell_nodes (nC, 8) int32): the unique active nodes and the
@@ -90,6 +102,7 @@ class TilePlan:
     @property
     def node_evaluations(self) -> int:
         """(receiver-independent) number of node kernel evaluations per receiver"""
+        self.ensure_tiles()
         return int(self.tile_n_nodes.sum())
 
     @property
@@ -218,31 +231,14 @@ def _best_brick(dims):
     return best[1]
 
 
-def build_tile_plan_tensor(axis_nodes, active_index=None) -> TilePlan:
-    """
-    O(n) planner for tensor meshes: pure index arithmetic, done natively by
-    ``pf_plan_tensor_count`` / ``pf_plan_tensor_fill`` (csrc/pf_plan.cu).
-
-    Parameters
-    ----------
-    axis_nodes : (nodes_x, nodes_y, nodes_z) 1-D node coordinates of the mesh
-    active_index : int array of the ACTIVE cells' mesh indices (F-order), ascending,
-        or None when every cell is active.  Column k of G is active cell k.
-    """
+def _tensor_tiles(xs, ys, zs, act):
+    """Brick tile arrays of a tensor mesh (native planner, csrc/pf_plan.cu)."""
     import ctypes
 
     from . import _lib
 
     lib = _lib.load_library()
-    xs, ys, zs = (np.ascontiguousarray(a, dtype=np.float64) for a in axis_nodes)
     nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
-    act = None if active_index is None else np.ascontiguousarray(active_index, dtype=np.int64)
-    n_cells = nx * ny * nz if act is None else act.size
-    if n_cells == 0:
-        return TilePlan(0, 0, np.zeros((0, 3, TILE_NODES)), np.zeros((0, TILE_CELLS, 8), np.uint16),
-                        np.zeros((0, TILE_CELLS), np.int32), np.zeros(0, np.int32), "empty")
-    if n_cells >= 2**31:
-        raise ValueError("more than 2^31-1 active cells are not supported")
     bx, by, bz = _best_brick((nx, ny, nz))
     n_bricks = (-(-nx // bx)) * (-(-ny // by)) * (-(-nz // bz))
     used = np.zeros(n_bricks, dtype=np.uint8)
@@ -257,21 +253,59 @@ def build_tile_plan_tensor(axis_nodes, active_index=None) -> TilePlan:
     _lib.check(lib.pf_plan_tensor_fill(nx, ny, nz, ptr(xs), ptr(ys), ptr(zs), bx, by, bz, ptr(act),
                                        n_act, ptr(used), n_tiles, ptr(tile_xyz), ptr(tile_cell_nodes),
                                        ptr(tile_cell_col), ptr(tile_n_nodes)), "pf_plan_tensor_fill")
+    return int(n_tiles), tile_xyz, tile_cell_nodes, tile_cell_col, tile_n_nodes
+
+
+def build_tile_plan_tensor(axis_nodes, active_index=None, with_tiles=True) -> TilePlan:
+    """
+    O(n) planner for tensor meshes: pure index arithmetic, done natively by
+    ``pf_plan_tensor_count`` / ``pf_plan_tensor_fill`` (csrc/pf_plan.cu).
+
+    Parameters
+    ----------
+    axis_nodes : (nodes_x, nodes_y, nodes_z) 1-D node coordinates of the mesh
+    active_index : int array of the ACTIVE cells' mesh indices (F-order), ascending,
+        or None when every cell is active.  Column k of G is active cell k.
+    with_tiles : build the brick tile arrays now (True) or only when a kernel that needs
+        them is used (``TilePlan.ensure_tiles``); the z-marching kernel only needs the
+        footprints.
+    """
+    xs, ys, zs = (np.ascontiguousarray(a, dtype=np.float64) for a in axis_nodes)
+    nx, ny, nz = len(xs) - 1, len(ys) - 1, len(zs) - 1
+    act = None if active_index is None else np.ascontiguousarray(active_index, dtype=np.int64)
+    n_cells = nx * ny * nz if act is None else act.size
+    if n_cells == 0:
+        return TilePlan(0, 0, np.zeros((0, 3, TILE_NODES)), np.zeros((0, TILE_CELLS, 8), np.uint16),
+                        np.zeros((0, TILE_CELLS), np.int32), np.zeros(0, np.int32), "empty")
+    if n_cells >= 2**31:
+        raise ValueError("more than 2^31-1 active cells are not supported")
     colmap = None
     if act is not None:
         colmap = np.full(nx * ny * nz, -1, dtype=np.int32)
         colmap[act] = np.arange(act.size, dtype=np.int32)
-    plan = TilePlan(int(n_tiles), int(n_cells), tile_xyz, tile_cell_nodes, tile_cell_col,
-                    tile_n_nodes, "tensor", grid_shape=(nx, ny, nz), grid_axes=(xs, ys, zs),
-                    grid_colmap=colmap, active_index=act)
+    plan = TilePlan(0, int(n_cells), None, None, None, None, "tensor", grid_shape=(nx, ny, nz),
+                    grid_axes=(xs, ys, zs), grid_colmap=colmap, active_index=act)
+    # node slots per receiver of the brick decomposition (without building it)
+    bx, by, bz = _best_brick((nx, ny, nz))
+    brick_slots = 0.0
+    for sx, cx in _axis_parts(nx, bx):
+        for sy, cy in _axis_parts(ny, by):
+            for sz, cz in _axis_parts(nz, bz):
+                brick_slots += cx * cy * cz * (-(-((sx + 1) * (sy + 1) * (sz + 1)) // _ROUND) * _ROUND)
     # keep a footprint set only if it evaluates fewer node slots per cell than the bricks
-    brick_slots = float((-(-tile_n_nodes.astype(np.int64) // _ROUND) * _ROUND).sum())
     for name, ncap in (("footprints4", 1024), ("footprints2", 512)):
         fps = march_footprints(nx, ny, nz, ncap, act)
         nodes = (fps[:, 2].astype(np.int64) + 1) * (fps[:, 3] + 1)
         slots = float(((-(-nodes // _ROUND) * _ROUND) * (fps[:, 5] - fps[:, 4] + 1)).sum())
         setattr(plan, name, fps if slots < 0.95 * brick_slots else np.zeros((0, 6), np.int32))
+    if with_tiles:
+        plan.ensure_tiles()
     return plan
+
+
+def _axis_parts(d, b):
+    full, rem = divmod(d, b)
+    return [(b, full)] + ([(rem, 1)] if rem else [])
 
 
 def march_footprints(nx, ny, nz, ncap, active_index=None):

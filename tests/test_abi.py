@@ -48,7 +48,7 @@ def test_argument_errors_are_status_codes():
     assert st == -2
     with pytest.raises(NotImplementedError):
         _lib.check(st, "pf_build_G")
-    bad = _lib.PfPlan(n_tiles=0, n_cells=0, tile_cells=256, tile_nodes=768)
+    bad = _lib.PfPlan(n_tiles=1, n_cells=1, tile_cells=256, tile_nodes=768)
     job.components[0] = _lib.GRAVITY_COMPONENTS["gz"]
     assert lib.pf_build_G(ctypes.byref(bad), ctypes.byref(job), None, 0, 0, None) == -1
     # empty problems are fine without touching the device
