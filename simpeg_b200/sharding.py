@@ -140,4 +140,4 @@ class Collectives:
             padded[: local.numel()] = local
         gathered = torch.empty(m * self.world_size, dtype=local.dtype, device=local.device)
         self._dist.all_gather_into_tensor(gathered, padded, group=self.group)
-        return gathered if index is None else gathered[self._index_cache[1]]
+        return gathered[: sharding.nD] if index is None else gathered[self._index_cache[1]]
