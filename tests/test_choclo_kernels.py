@@ -120,3 +120,37 @@ def test_gravity_point_mass_limit():
     d = np.array([0.0, 0.0, -100.0]) - p
     expected = constants.G * 1e8 * d[2] / np.linalg.norm(d) ** 3
     assert gz == pytest.approx(expected, rel=1e-4)
+
+
+@pytest.mark.parametrize("name", ["e", "n", "u", "ee", "nn", "uu", "en", "eu", "nu",
+                                  "eee", "nnn", "uuu", "een", "eeu", "enn", "nnu", "euu", "nuu", "enu"])
+def test_singular_branches_are_the_continuous_limits(name):
+    """
+    The branches of safe_log / safe_atan2 / kernel_iii / kernel_iij that fire when the
+    observation point is aligned with prism vertices, edges or faces are restated from memory of
+    choclo (parity unpinned against the real package).  Physics pins them instead: outside the
+    prism every component of the field is continuous, so the prism sum AT an aligned point must
+    equal its limit from nearby points.  The limit is taken from symmetric pairs 1e-2 m and
+    5e-3 m away with one Richardson step (error O(h^4)); closer points are useless because the
+    reference formulas themselves lose all digits there (r + x cancels below 1e-7 m).
+    """
+    w, e, s, n, b, t = PRISM
+    aligned = [
+        np.array([w, 0.2, 1.0]),          # above the plane of the west face (e == 0 for 4 vertices)
+        np.array([0.3, n, 1.0]),          # plane of the north face
+        np.array([w, s, 2.0]),            # straight above a vertical edge (e == n == 0)
+        np.array([e, n, 0.5]),            # above another vertical edge
+        np.array([4.0, 0.1, t]),          # level with the top face, outside (u == 0)
+        np.array([4.0, n, t]),            # on the line of a horizontal edge, outside (n == u == 0)
+        np.array([w, -5.0, b]),           # on the line of another edge, outside (e == u == 0)
+    ]
+    shift = np.array([1.0, -0.7, 0.4])
+
+    def mean_at(p, h):
+        return 0.5 * (prism_sum(name, p + h * shift) + prism_sum(name, p - h * shift))
+
+    for p in aligned:
+        at = prism_sum(name, p)
+        limit = (4.0 * mean_at(p, 5e-3) - mean_at(p, 1e-2)) / 3.0
+        assert np.isfinite(at)
+        assert at == pytest.approx(limit, abs=5e-7), (name, p)
