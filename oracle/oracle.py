@@ -370,6 +370,165 @@ class OracleSimulation:
 
 
 # ---------------------------------------------------------------------------
+# Equivalent-source layer (SimulationEquivalentSourceLayer)
+# ---------------------------------------------------------------------------
+class _CLayerBackend:
+    """Layer loops of pf_oracle.c (pfo_layer_gravity / pfo_layer_mag)."""
+
+    def __init__(self, parallel=True):
+        self.lib = _library()
+        self.parallel = int(bool(parallel))
+
+    def gravity(self, mode, receivers, bounds, top, bottom, component, factor, G_view=None,
+                vec=None, out=None):
+        gp, gs, f32 = (None, _i64(0), 0) if G_view is None else \
+            (*_CBackend._view(G_view), int(G_view.dtype == np.float32))
+        vp, vs = (None, _i64(0)) if vec is None else _CBackend._view(vec)
+        op, os_ = (None, _i64(0)) if out is None else _CBackend._view(out)
+        self.lib.pfo_layer_gravity(
+            ctypes.c_int(mode), _p(receivers), _i64(receivers.shape[0]), _p(bounds), _p(top),
+            _p(bottom), _i64(bounds.shape[0]), gp, gs, ctypes.c_int(f32), vp, vs, op, os_,
+            ctypes.c_int(KERNEL_ID[GRAVITY_KERNELS[component]]), ctypes.c_double(factor),
+            ctypes.c_int(self.parallel))
+
+    def mag(self, mode, receivers, bounds, top, bottom, component, b0, scalar, G_view=None,
+            vec=None, out=None):
+        gp, gs, f32 = (None, _i64(0), 0) if G_view is None else \
+            (*_CBackend._view(G_view), int(G_view.dtype == np.float32))
+        vp, vs = (None, _i64(0)) if vec is None else _CBackend._view(vec)
+        op, os_ = (None, _i64(0)) if out is None else _CBackend._view(out)
+        kids, nk = _CBackend._kids(MAGNETIC_KERNELS[component])
+        # forward of "tmi" and of the b components goes through choclo's own forward functions
+        choclo_forward = int(component == "tmi" or len(MAGNETIC_KERNELS[component]) == 3)
+        self.lib.pfo_layer_mag(
+            ctypes.c_int(mode), _p(receivers), _i64(receivers.shape[0]), _p(bounds), _p(top),
+            _p(bottom), _i64(bounds.shape[0]), gp, gs, ctypes.c_int(f32), vp, vs, op, os_,
+            _p(b0), kids, nk, ctypes.c_int(int(scalar)), ctypes.c_int(choclo_forward),
+            ctypes.c_int(self.parallel))
+
+
+class _RefLayerBackend:
+    """The reference's own 2D-mesh numba loops; argument orders as the call sites
+    gravity/simulation.py:801-810, 849-857, 888-897, 929-938 and
+    magnetics/simulation.py:1320-1372, 1416-1466, 1505-1559, 1584-1651."""
+
+    def __init__(self, parallel=True):
+        from .ref_loader import load_reference_2d, reference_forward_tables, reference_kernel_tables
+
+        self.g2, self.m2 = load_reference_2d()
+        self.gf, self.mf = reference_forward_tables()
+        _, self.mk = reference_kernel_tables()
+        self.parallel = bool(parallel)
+
+    def gravity(self, mode, receivers, bounds, top, bottom, component, factor, G_view=None,
+                vec=None, out=None):
+        F = self.g2.NUMBA_FUNCTIONS_2D
+        fn = self.gf[component]
+        if mode == 0:
+            F["sensitivity"][self.parallel](receivers, bounds, top, bottom, G_view, fn, factor)
+        elif mode == 1:
+            F["forward"][self.parallel](receivers, bounds, top, bottom, vec, out, fn, factor)
+        elif mode == 2:
+            F["gt_dot_v"][self.parallel](receivers, bounds, top, bottom, fn, factor, vec, out)
+        else:
+            F["diagonal_gtg"][self.parallel](receivers, bounds, top, bottom, fn, factor, vec, out)
+
+    def mag(self, mode, receivers, bounds, top, bottom, component, b0, scalar, G_view=None,
+            vec=None, out=None):
+        F = self.m2.NUMBA_FUNCTIONS_2D
+        key = ["sensitivity", "forward", "gt_dot_v", "diagonal_gtg"][mode]
+        if component == "tmi":
+            fam, kargs = "tmi", []
+        elif component in ("tmi_x", "tmi_y", "tmi_z"):
+            fam, kargs = "tmi_derivative", list(self.mk[component])
+        else:
+            fam, kargs = "magnetic_component", list(self.mk[component])
+        fn = F[key][fam][self.parallel]
+        head = (receivers, bounds, top, bottom)
+        cf = 1 / 4 / np.pi
+        if mode == 0:
+            fn(*head, G_view, b0.copy(), *kargs, scalar)
+        elif mode == 1:
+            if fam == "magnetic_component":
+                kargs = [self.mf[component]]
+            fn(*head, vec, out, b0.copy(), *kargs, scalar)
+        elif mode == 2:
+            fn(*head, b0.copy(), *kargs, scalar, vec, out)
+        else:
+            fn(*head, b0.copy(), *kargs, cf, scalar, vec, out)
+
+
+class OracleLayerSimulation:
+    """
+    Reference-order CPU evaluation of the equivalent-source layer simulations
+    (gravity/simulation.py:727-939, magnetics/simulation.py:1235-1653).
+
+    Parameters
+    ----------
+    physics : "gravity" | "magnetics"
+    cell_bounds : (nC, 4) x_min, x_max, y_min, y_max of the active cells of the 2D mesh
+    top, bottom : (nC,) elevation of the top / bottom face of every cell
+    receiver_list, b0, model_type : as OracleSimulation
+    """
+
+    def __init__(self, physics, cell_bounds, top, bottom, receiver_list, b0=None,
+                 model_type="scalar", sensitivity_dtype=np.float64, backend="c", parallel=True):
+        self.physics = physics
+        self.bounds = np.ascontiguousarray(cell_bounds, dtype=np.float64).reshape(-1, 4)
+        self.nC = self.bounds.shape[0]
+        self.top = np.ascontiguousarray(np.broadcast_to(top, (self.nC,)), dtype=np.float64)
+        self.bottom = np.ascontiguousarray(np.broadcast_to(bottom, (self.nC,)), dtype=np.float64)
+        self.receiver_list = [
+            (np.ascontiguousarray(loc, dtype=np.float64),
+             [comps] if isinstance(comps, str) else list(comps))
+            for loc, comps in receiver_list
+        ]
+        self.b0 = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
+        self.scalar = model_type == "scalar"
+        self.dtype = sensitivity_dtype
+        self.nP = self.nC if (physics == "gravity" or self.scalar) else 3 * self.nC
+        self.nD = sum(loc.shape[0] * len(c) for loc, c in self.receiver_list)
+        self.backend = _CLayerBackend(parallel) if backend == "c" else _RefLayerBackend(parallel)
+
+    _iter = OracleSimulation._iter
+
+    def _call(self, mode, receivers, component, **kw):
+        head = (mode, receivers, self.bounds, self.top, self.bottom, component)
+        if self.physics == "gravity":
+            self.backend.gravity(*head, gravity_conversion_factor(component), **kw)
+        else:
+            self.backend.mag(*head, self.b0, self.scalar, **kw)
+
+    def sensitivity_matrix(self):
+        G = np.empty((self.nD, self.nP), dtype=self.dtype)
+        for receivers, component, sl in self._iter():
+            self._call(0, receivers, component, G_view=G[sl, :])
+        return G
+
+    def forward(self, model):
+        model = np.ascontiguousarray(model, dtype=np.float64)
+        fields = np.zeros(self.nD, dtype=np.float64)
+        for receivers, component, sl in self._iter():
+            self._call(1, receivers, component, vec=model, out=fields[sl])
+        return fields
+
+    def gt_dot_v(self, vector):
+        vector = np.ascontiguousarray(vector, dtype=np.float64)
+        result = np.zeros(self.nP, dtype=np.float64)
+        for receivers, component, sl in self._iter():
+            self._call(2, receivers, component, vec=vector[sl], out=result)
+        return result
+
+    def diag_gtg(self, weights):
+        """Whole weights array per component, indexed by receiver (reference quirk)."""
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        diagonal = np.zeros(self.nP, dtype=np.float64)
+        for receivers, component, _ in self._iter():
+            self._call(3, receivers, component, vec=weights, out=diagonal)
+        return diagonal
+
+
+# ---------------------------------------------------------------------------
 # numpy tensor-mesh (nodes, cell_nodes) exactly as base.py:120-141 / discretize
 # ---------------------------------------------------------------------------
 def tensor_mesh_arrays(hx, hy, hz, origin):

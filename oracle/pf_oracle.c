@@ -506,3 +506,244 @@ void pfo_mag_diag_gtg(const double *receivers, int64_t R,
         free(k);
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* Equivalent-source layer (2D mesh + top/bottom per cell)             */
+/*   simpeg/potential_fields/gravity/_numba/_2d_mesh.py                */
+/*   simpeg/potential_fields/magnetics/_numba/_2d_mesh.py              */
+/*   simpeg/potential_fields/_numba_utils.py:48-255                    */
+/* Cells are prisms given by bounds (x_min, x_max, y_min, y_max),      */
+/* bottom and top; nothing is shared between cells.                    */
+/* ------------------------------------------------------------------ */
+
+/* evaluate_kernels_on_cell / evaluate_six_kernels_on_cell (and choclo's
+ * _evaluate_kernel): signed sum over the 8 shifted vertices, east / north /
+ * top first, sign (-1)^(i+j+k). */
+static void eval_cell(const double *rx, const double *b4, double bottom, double top,
+                      const int *kids, int nk, double *out)
+{
+    for (int q = 0; q < nk; ++q) out[q] = 0.0;
+    for (int i = 0; i < 2; ++i) {
+        double se = (i == 0 ? b4[1] : b4[0]) - rx[0];
+        double se2 = se * se;
+        for (int j = 0; j < 2; ++j) {
+            double sn = (j == 0 ? b4[3] : b4[2]) - rx[1];
+            double sn2 = sn * sn;
+            for (int k = 0; k < 2; ++k) {
+                double su = (k == 0 ? top : bottom) - rx[2];
+                double su2 = su * su;
+                double radius = sqrt(se2 + sn2 + su2);
+                double sign = ((i + j + k) & 1) ? -1.0 : 1.0;
+                for (int q = 0; q < nk; ++q)
+                    out[q] += sign * eval_kernel(kids[q], se, sn, su, radius);
+            }
+        }
+    }
+}
+
+#define PFO_GRAVITATIONAL_CONST 6.6743e-11            /* choclo.constants */
+#define PFO_VACUUM_MAGNETIC_PERMEABILITY 1.25663706212e-6
+
+/* choclo.prism.gravity_* (density * G * vertex sum); "guv" is
+ * gravity/simulation.py:33-70 gravity_uv = 0.5 * (gravity_nn - gravity_ee) */
+static double layer_gravity_forward_func(int kid, const double *rx, const double *b4,
+                                         double bottom, double top, double density)
+{
+    double s;
+    if (kid == K_UV) {
+        int k_nn = K_NN, k_ee = K_EE;
+        double a, b;
+        eval_cell(rx, b4, bottom, top, &k_nn, 1, &a);
+        eval_cell(rx, b4, bottom, top, &k_ee, 1, &b);
+        return 0.5 * (PFO_GRAVITATIONAL_CONST * density * a - PFO_GRAVITATIONAL_CONST * density * b);
+    }
+    eval_cell(rx, b4, bottom, top, &kid, 1, &s);
+    return PFO_GRAVITATIONAL_CONST * density * s;
+}
+
+/* mode 0: _sensitivity_gravity (97-160), 1: _forward_gravity (21-94),
+ * 2: _g_t_dot_v_{serial,parallel} (163-295), 3: _diagonal_G_T_dot_G_* (298-434;
+ * same weights[i] quirk as the 3D loops). */
+void pfo_layer_gravity(int mode, const double *receivers, int64_t R,
+                       const double *bounds, const double *top, const double *bottom, int64_t nC,
+                       void *G, int64_t row_stride, int f32,
+                       const double *vec, int64_t vstride, double *out, int64_t ostride,
+                       int kid, double constant_factor, int parallel)
+{
+#pragma omp parallel if (parallel)
+    {
+        double *priv = (mode >= 2) ? (double *)calloc((size_t)nC, sizeof(double)) : NULL;
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < R; ++i) {
+            const double *rx = receivers + 3 * i;
+            double acc = (mode == 1) ? out[i * ostride] : 0.0;
+            for (int64_t j = 0; j < nC; ++j) {
+                /* forward: density; gt_dot_v: the reference passes vector[i] as the density */
+                double dens = (mode == 1) ? vec[j] : (mode == 2 ? vec[i * vstride] : 1.0);
+                double g = constant_factor
+                           * layer_gravity_forward_func(kid, rx, bounds + 4 * j, bottom[j], top[j], dens);
+                if (mode == 0) {
+                    if (f32) ((float *)G)[i * row_stride + j] = (float)g;
+                    else ((double *)G)[i * row_stride + j] = g;
+                } else if (mode == 1) {
+                    acc += g;
+                } else if (mode == 2) {
+                    priv[j] += g;
+                } else {
+                    priv[j] += vec[i] * (g * g);
+                }
+            }
+            if (mode == 1) out[i * ostride] = acc;
+        }
+        if (mode >= 2) {
+            reduce_private(out, priv, nC);
+            free(priv);
+        }
+    }
+}
+
+/* Magnetics.  family 3 = "magnetic_component" (three kernels), 6 = "tmi" /
+ * "tmi_derivative" (six kernels xx,yy,zz,xy,xz,yz).  use_choclo_forward != 0
+ * selects, for mode 1, the reference's forward loops that call choclo's own
+ * forward functions: _forward_mag (24-147, choclo.prism.magnetic_*) and
+ * _forward_tmi (150-266, choclo.prism.magnetic_field), which scale by
+ * mu0/4pi inside choclo and divide by mu0 afterwards; otherwise
+ * _forward_tmi_derivative (269-431). */
+void pfo_layer_mag(int mode, const double *receivers, int64_t R,
+                   const double *bounds, const double *top, const double *bottom, int64_t nC,
+                   void *G, int64_t row_stride, int f32,
+                   const double *vec, int64_t vstride, double *out, int64_t ostride,
+                   const double *b0, const int *kids, int nk, int scalar_model,
+                   int use_choclo_forward, int parallel)
+{
+    field_t f = unit_field(b0);
+    const double constant_factor = 1.0 / 4 / M_PI;
+    const int64_t nP = scalar_model ? nC : 3 * nC;
+#pragma omp parallel if (parallel)
+    {
+        double *priv = (mode >= 2) ? (double *)calloc((size_t)nP, sizeof(double)) : NULL;
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < R; ++i) {
+            const double *rx = receivers + 3 * i;
+            double acc = (mode == 1) ? out[i * ostride] : 0.0;
+            for (int64_t j = 0; j < nC; ++j) {
+                const double *b4 = bounds + 4 * j;
+                if (mode == 1 && use_choclo_forward) {
+                    double mx, my, mz;
+                    if (scalar_model) {
+                        mx = vec[j] * f.fx; my = vec[j] * f.fy; mz = vec[j] * f.fz;
+                    } else {
+                        mx = vec[j]; my = vec[j + nC]; mz = vec[j + 2 * nC];
+                    }
+                    /* per vertex: M . kernels, summed with the sign; then mu0/4pi */
+                    double sums[3] = {0.0, 0.0, 0.0};
+                    const int ncomp = (nk == 3) ? 1 : 3;
+                    /* kernel triplets of (b_e, b_n, b_u) in terms of xx,yy,zz,xy,xz,yz */
+                    for (int a = 0; a < 2; ++a) {
+                        double se = (a == 0 ? b4[1] : b4[0]) - rx[0];
+                        double se2 = se * se;
+                        for (int b = 0; b < 2; ++b) {
+                            double sn = (b == 0 ? b4[3] : b4[2]) - rx[1];
+                            double sn2 = sn * sn;
+                            for (int c = 0; c < 2; ++c) {
+                                double su = (c == 0 ? top[j] : bottom[j]) - rx[2];
+                                double su2 = su * su;
+                                double radius = sqrt(se2 + sn2 + su2);
+                                double sign = ((a + b + c) & 1) ? -1.0 : 1.0;
+                                if (ncomp == 1) {
+                                    sums[0] += sign * (mx * eval_kernel(kids[0], se, sn, su, radius)
+                                                       + my * eval_kernel(kids[1], se, sn, su, radius)
+                                                       + mz * eval_kernel(kids[2], se, sn, su, radius));
+                                } else {
+                                    double kxx = eval_kernel(kids[0], se, sn, su, radius);
+                                    double kyy = eval_kernel(kids[1], se, sn, su, radius);
+                                    double kzz = eval_kernel(kids[2], se, sn, su, radius);
+                                    double kxy = eval_kernel(kids[3], se, sn, su, radius);
+                                    double kxz = eval_kernel(kids[4], se, sn, su, radius);
+                                    double kyz = eval_kernel(kids[5], se, sn, su, radius);
+                                    sums[0] += sign * (mx * kxx + my * kxy + mz * kxz);
+                                    sums[1] += sign * (mx * kxy + my * kyy + mz * kyz);
+                                    sums[2] += sign * (mx * kxz + my * kyz + mz * kzz);
+                                }
+                            }
+                        }
+                    }
+                    const double c_m = PFO_VACUUM_MAGNETIC_PERMEABILITY / 4 / M_PI;
+                    if (ncomp == 1) {
+                        acc += f.amp * (c_m * sums[0]) / PFO_VACUUM_MAGNETIC_PERMEABILITY;
+                    } else {
+                        double bx = c_m * sums[0], by = c_m * sums[1], bz = c_m * sums[2];
+                        acc += f.amp * (bx * f.fx + by * f.fy + bz * f.fz)
+                               / PFO_VACUUM_MAGNETIC_PERMEABILITY;
+                    }
+                    continue;
+                }
+                double u[6];
+                eval_cell(rx, b4, bottom[j], top[j], kids, nk, u);
+                double bx, by, bz;
+                if (mode == 1 && nk == 6 && !scalar_model) {
+                    /* _forward_tmi_derivative, vector model: b = U m, then f . b */
+                    double m_x = vec[j], m_y = vec[j + nC], m_z = vec[j + 2 * nC];
+                    bx = u[0] * m_x + u[3] * m_y + u[4] * m_z;
+                    by = u[3] * m_x + u[1] * m_y + u[5] * m_z;
+                    bz = u[4] * m_x + u[5] * m_y + u[2] * m_z;
+                    acc += f.amp * (bx * f.fx + by * f.fy + bz * f.fz) / 4 / M_PI;
+                    continue;
+                }
+                if (nk == 3) {
+                    bx = u[0]; by = u[1]; bz = u[2];
+                } else {
+                    bx = u[0] * f.fx + u[3] * f.fy + u[4] * f.fz;
+                    by = u[3] * f.fx + u[1] * f.fy + u[5] * f.fz;
+                    bz = u[4] * f.fx + u[5] * f.fy + u[2] * f.fz;
+                }
+                if (mode == 0) {
+                    double g0, g1 = 0, g2 = 0;
+                    if (scalar_model) {
+                        g0 = constant_factor * f.amp * (bx * f.fx + by * f.fy + bz * f.fz);
+                    } else {
+                        g0 = constant_factor * f.amp * bx;
+                        g1 = constant_factor * f.amp * by;
+                        g2 = constant_factor * f.amp * bz;
+                    }
+                    if (f32) {
+                        float *row = (float *)G + i * row_stride;
+                        row[j] = (float)g0;
+                        if (!scalar_model) { row[j + nC] = (float)g1; row[j + 2 * nC] = (float)g2; }
+                    } else {
+                        double *row = (double *)G + i * row_stride;
+                        row[j] = g0;
+                        if (!scalar_model) { row[j + nC] = g1; row[j + 2 * nC] = g2; }
+                    }
+                } else if (mode == 1) {
+                    /* _forward_tmi_derivative, scalar model (405-421) */
+                    acc += vec[j] * f.amp * (f.fx * bx + f.fy * by + f.fz * bz) / (4 * M_PI);
+                } else if (mode == 2) {
+                    double v = vec[i * vstride];
+                    if (scalar_model) {
+                        priv[j] += constant_factor * v * f.amp * (bx * f.fx + by * f.fy + bz * f.fz);
+                    } else {
+                        priv[j] += constant_factor * v * f.amp * bx;
+                        priv[j + nC] += constant_factor * v * f.amp * by;
+                        priv[j + 2 * nC] += constant_factor * v * f.amp * bz;
+                    }
+                } else {
+                    if (scalar_model) {
+                        double g = constant_factor * f.amp * (bx * f.fx + by * f.fy + bz * f.fz);
+                        priv[j] += vec[i] * (g * g);
+                    } else {
+                        double cst = constant_factor * f.amp;
+                        priv[j] += vec[i] * ((cst * bx) * (cst * bx));
+                        priv[j + nC] += vec[i] * ((cst * by) * (cst * by));
+                        priv[j + 2 * nC] += vec[i] * ((cst * bz) * (cst * bz));
+                    }
+                }
+            }
+            if (mode == 1) out[i * ostride] = acc;
+        }
+        if (mode >= 2) {
+            reduce_private(out, priv, nP);
+            free(priv);
+        }
+    }
+}

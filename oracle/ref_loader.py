@@ -79,6 +79,61 @@ def load_reference():
     return _loaded
 
 
+_loaded_2d = None
+
+
+def load_reference_2d():
+    """
+    ``(gravity_2d, magnetics_2d)``: the reference's equivalent-source layer loop files
+    ``gravity/_numba/_2d_mesh.py`` and ``magnetics/_numba/_2d_mesh.py`` (each exposing
+    ``NUMBA_FUNCTIONS_2D``), executed unmodified on the choclo shim.
+    """
+    global _loaded_2d
+    if _loaded_2d is None:
+        load_reference()
+        pf = REFERENCE_ROOT / "simpeg" / "potential_fields"
+        grav = _exec("refpf.gravity._numba._2d_mesh", pf / "gravity" / "_numba" / "_2d_mesh.py")
+        mag = _exec("refpf.magnetics._numba._2d_mesh", pf / "magnetics" / "_numba" / "_2d_mesh.py")
+        _loaded_2d = (grav, mag)
+    return _loaded_2d
+
+
+def reference_forward_tables():
+    """
+    component -> choclo forward function, as gravity/simulation.py:87-98 (with ``gravity_uv``
+    of lines 33-70 rebuilt on the shim) and magnetics/simulation.py:104-114.
+    """
+    from numba import jit
+
+    choclo, _, _ = load_reference()
+    p = choclo.prism
+    gravity_nn, gravity_ee = p.gravity_nn, p.gravity_ee
+
+    @jit(nopython=True)
+    def gravity_uv(easting, northing, upward, prism_west, prism_east, prism_south, prism_north,
+                   prism_bottom, prism_top, density):
+        result = 0.5 * (
+            gravity_nn(easting, northing, upward, prism_west, prism_east, prism_south,
+                       prism_north, prism_bottom, prism_top, density)
+            - gravity_ee(easting, northing, upward, prism_west, prism_east, prism_south,
+                         prism_north, prism_bottom, prism_top, density)
+        )
+        return result
+
+    gravity = {
+        "gx": p.gravity_e, "gy": p.gravity_n, "gz": p.gravity_u,
+        "gxx": p.gravity_ee, "gyy": p.gravity_nn, "gzz": p.gravity_uu,
+        "gxy": p.gravity_en, "gxz": p.gravity_eu, "gyz": p.gravity_nu,
+        "guv": gravity_uv,
+    }
+    magnetics = {
+        "bx": p.magnetic_e, "by": p.magnetic_n, "bz": p.magnetic_u,
+        "bxx": p.magnetic_ee, "byy": p.magnetic_nn, "bzz": p.magnetic_uu,
+        "bxy": p.magnetic_en, "bxz": p.magnetic_eu, "byz": p.magnetic_nu,
+    }
+    return gravity, magnetics
+
+
 def reference_kernel_tables():
     """
     The component -> choclo kernel tables of the reference's simulation.py

@@ -56,10 +56,17 @@ __device__ __forceinline__ double warp_sum(double v)
 // shuffle reduction, one shared-memory slot per (warp, row).
 // ---------------------------------------------------------------------------
 constexpr int GEMV_ROWS = 32;
-// 128-bit vectors of x kept per thread: 4 for fp64 G (8 doubles); 2 for fp32 G (8 floats ->
-// 8 doubles after conversion), so that both variants stay near 60 registers / 4 CTAs per SM
+// 128-bit vectors of G per thread and row (independent loads in flight): 4 for both storage
+// types (fp64: 8 doubles of x in registers; fp32: 16 floats of x)
 template <typename GT> struct GemvKx { static constexpr int N = 4; };
-template <> struct GemvKx<float> { static constexpr int N = 2; };
+
+// fp32 storage follows the reference's arithmetic for the products themselves -- it casts the
+// vector to the storage type and multiplies in fp32 (gravity/simulation.py:387,418
+// `.astype(self.sensitivity_dtype)`; BLAS sgemv) -- but only over the 4 elements of one 128-bit
+// load; every such partial is then accumulated in fp64.  One fp32->fp64 conversion (XU pipe) per
+// load instead of one per element: the conversion pipe was what held the fp32 products at 5.3 TB/s.
+template <typename GT> struct XType { using type = double; };
+template <> struct XType<float> { using type = float; };
 
 template <typename GT, bool ALIGNED>
 __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G, int64_t rows, int64_t cols,
@@ -69,6 +76,7 @@ __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G,
     constexpr int VN = Vec<GT>::N;
     constexpr int GEMV_KX = GemvKx<GT>::N;
     using VT = typename Vec<GT>::type;
+    using XT = typename XType<GT>::type;
     constexpr int CHUNK = THREADS * VN * GEMV_KX;
     __shared__ double wpart[WARPS][GEMV_ROWS];
 
@@ -77,33 +85,41 @@ __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G,
     const int64_t r0 = (int64_t)blockIdx.y * GEMV_ROWS;
     const int nrows = (int)min((int64_t)GEMV_ROWS, rows - r0);
 
-    double xr[GEMV_KX][VN];
+    XT xr[GEMV_KX][VN];
 #pragma unroll
     for (int k = 0; k < GEMV_KX; ++k)
 #pragma unroll
         for (int v = 0; v < VN; ++v) {
             const int64_t c = c0 + ((int64_t)k * THREADS + tid) * VN + v;
-            xr[k][v] = (c < cols) ? x[c] : 0.0;
+            xr[k][v] = (c < cols) ? (XT)x[c] : (XT)0;
         }
 
     for (int i = 0; i < nrows; ++i) {
         const GT *row = G + (r0 + i) * ld;
-        double g[GEMV_KX][VN];
+        GT g[GEMV_KX][VN];
 #pragma unroll
         for (int k = 0; k < GEMV_KX; ++k) {
             const int64_t c = c0 + ((int64_t)k * THREADS + tid) * VN;
             if (ALIGNED && c + VN <= cols) {
-                Vec<GT>::unpack(ld_stream(reinterpret_cast<const VT *>(row + c)), g[k]);
+                Vec<GT>::unpack_native(ld_stream(reinterpret_cast<const VT *>(row + c)), g[k]);
             } else {
 #pragma unroll
-                for (int v = 0; v < VN; ++v) g[k][v] = (c + v < cols) ? (double)row[c + v] : 0.0;
+                for (int v = 0; v < VN; ++v) g[k][v] = (c + v < cols) ? row[c + v] : (GT)0;
             }
         }
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < GEMV_KX; ++k)
+        for (int k = 0; k < GEMV_KX; ++k) {
+            if constexpr (sizeof(GT) == 4) {
+                float p = g[k][0] * xr[k][0];
 #pragma unroll
-            for (int v = 0; v < VN; ++v) s = fma(g[k][v], xr[k][v], s);
+                for (int v = 1; v < VN; ++v) p = fmaf(g[k][v], xr[k][v], p);
+                s += (double)p;
+            } else {
+#pragma unroll
+                for (int v = 0; v < VN; ++v) s = fma(g[k][v], xr[k][v], s);
+            }
+        }
         s = warp_sum(s);
         if ((tid & 31) == 0) wpart[tid >> 5][i] = s;
     }
@@ -200,16 +216,33 @@ __global__ void __launch_bounds__(THREADS) column_kernel(const GT *__restrict__ 
                 load_row(G + (i + u) * ld, g[u]);
                 yy[u] = __ldg(yv + i + u);
             }
+            if constexpr (MODE == 0 && sizeof(GT) == 4) {
+                // fp32 products of the COL_UNROLL rows (the reference multiplies in the storage
+                // type), one conversion per column and row group, fp64 accumulation over groups
+                float y32[COL_UNROLL];
 #pragma unroll
-            for (int u = 0; u < COL_UNROLL; ++u)
+                for (int u = 0; u < COL_UNROLL; ++u) y32[u] = (float)yy[u];
 #pragma unroll
                 for (int k = 0; k < COL_KC; ++k)
 #pragma unroll
                     for (int v = 0; v < VN; ++v) {
-                        const double gv = (double)g[u][k][v];
-                        if (MODE == 0) acc[k][v] = fma(yy[u], gv, acc[k][v]);
-                        else acc[k][v] = fma(yy[u], gv * gv, acc[k][v]);
+                        float p = y32[0] * g[0][k][v];
+#pragma unroll
+                        for (int u = 1; u < COL_UNROLL; ++u) p = fmaf(y32[u], g[u][k][v], p);
+                        acc[k][v] += (double)p;
                     }
+            } else {
+#pragma unroll
+                for (int u = 0; u < COL_UNROLL; ++u)
+#pragma unroll
+                    for (int k = 0; k < COL_KC; ++k)
+#pragma unroll
+                        for (int v = 0; v < VN; ++v) {
+                            const double gv = (double)g[u][k][v];
+                            if (MODE == 0) acc[k][v] = fma(yy[u], gv, acc[k][v]);
+                            else acc[k][v] = fma(yy[u], gv * gv, acc[k][v]);
+                        }
+            }
         }
         for (; i < r1; ++i) {
             GT g[COL_KC][VN];

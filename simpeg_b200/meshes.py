@@ -33,24 +33,37 @@ def _unpack_h(h):
 
 
 class TensorMesh:
-    """3-D tensor mesh.  ``origin`` is a 3-vector or a discretize-style string
-    of 'C' (centred), 'N' (negative: top/right edge at 0) or '0' per axis."""
+    """3-D tensor mesh (2-D for the equivalent-source layer simulations, which only read ``dim``,
+    ``n_cells``, ``cell_bounds`` and the node axes).  ``origin`` is a vector or a discretize-style
+    string of 'C' (centred), 'N' (negative: top/right edge at 0) or '0' per axis."""
 
     _meshType = "TENSOR"
 
     def __init__(self, h, origin=None):
-        if len(h) != 3:
-            raise ValueError("only 3-D tensor meshes are supported")
+        if len(h) not in (2, 3):
+            raise ValueError("only 2-D and 3-D tensor meshes are supported")
         self.h = [_unpack_h(hi) for hi in h]
         if origin is None:
-            origin = np.zeros(3)
+            origin = np.zeros(len(h))
         if isinstance(origin, str):
             o = []
             for ch, hi in zip(origin, self.h):
                 o.append({"0": 0.0, "C": -hi.sum() / 2.0, "N": -hi.sum()}[ch])
             origin = o
         self.origin = np.asarray(origin, dtype=np.float64)
-        self.dim = 3
+        self.dim = len(self.h)
+
+    @property
+    def cell_bounds(self):
+        """(n_cells, 2 dim) lower / upper bound of every cell per axis: x_min, x_max, y_min,
+        y_max[, z_min, z_max], cells x fastest (``discretize`` ``cell_bounds``)."""
+        axes = [self.origin[d] + np.r_[0.0, np.cumsum(self.h[d])] for d in range(self.dim)]
+        lo = np.meshgrid(*[a[:-1] for a in axes], indexing="ij")
+        hi = np.meshgrid(*[a[1:] for a in axes], indexing="ij")
+        cols = []
+        for d in range(self.dim):
+            cols += [lo[d].reshape(-1, order="F"), hi[d].reshape(-1, order="F")]
+        return np.ascontiguousarray(np.stack(cols, axis=1))
 
     @property
     def shape_cells(self):
@@ -80,6 +93,8 @@ class TensorMesh:
 
     @property
     def nodes_z(self):
+        if self.dim < 3:
+            raise AttributeError("a 2-D tensor mesh has no z axis")
         return self.origin[2] + np.r_[0.0, np.cumsum(self.h[2])]
 
     @staticmethod
@@ -121,6 +136,23 @@ class TensorMesh:
                 inds[1:, 1:, 1:].reshape(-1, order="F"),
             ], axis=-1)
         return self._cell_nodes
+
+
+class CellBoundsMesh2D:
+    """A 2-D mesh known only by its cells (stand-in for a 2-D ``discretize.TreeMesh`` in the
+    equivalent-source layer simulations): ``cell_bounds`` (n_cells, 4) = x_min, x_max, y_min, y_max."""
+
+    _meshType = "TREE"
+
+    def __init__(self, cell_bounds):
+        self.cell_bounds = np.ascontiguousarray(cell_bounds, dtype=np.float64).reshape(-1, 4)
+        self.dim = 2
+
+    @property
+    def n_cells(self):
+        return int(self.cell_bounds.shape[0])
+
+    nC = n_cells
 
 
 class TreeMesh:

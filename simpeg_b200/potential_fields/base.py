@@ -178,12 +178,14 @@ class BasePFSimulation:
 
     @mesh.setter
     def mesh(self, value):
-        for attr in ("dim", "n_cells", "cell_nodes"):
-            if not hasattr(value, attr):
-                raise TypeError(f"mesh must be a 3D tensor or tree mesh (missing {attr!r})")
+        if not hasattr(value, "dim"):
+            raise TypeError("mesh must be a 3D tensor or tree mesh (missing 'dim')")
         if value.dim != 3:
             raise ValueError(
                 f"{type(self).__name__} mesh must be 3D, received a {value.dim}D mesh.")
+        for attr in ("n_cells", "cell_nodes"):
+            if not hasattr(value, attr):
+                raise TypeError(f"mesh must be a 3D tensor or tree mesh (missing {attr!r})")
         self._mesh = value
 
     @property
@@ -432,3 +434,103 @@ class BasePFSimulation:
         if f is not None:
             return f
         return self.fields(m)
+
+
+def layer_nodes_and_cells(cell_bounds, cell_z_top, cell_z_bottom):
+    """
+    The prisms of an equivalent-source layer as an unstructured hexahedral "mesh" for the
+    node-sharing kernels: ``nodes (nN, 3)`` and ``cell_nodes (nC, 8)`` with the vertex order of
+    base.py:431-441 (x fastest, then y, then bottom before top).  Vertices that coincide -- all of
+    them in the horizontal directions when top and bottom are constant -- are stored once, so a
+    flat layer costs ~2 node evaluations per (receiver, cell) pair instead of the 8 of the
+    reference's per-cell loops (``_numba_utils.py:48-255``).
+    """
+    b = np.ascontiguousarray(cell_bounds, dtype=np.float64).reshape(-1, 4)
+    n = b.shape[0]
+    top = np.ascontiguousarray(cell_z_top, dtype=np.float64).reshape(n)
+    bot = np.ascontiguousarray(cell_z_bottom, dtype=np.float64).reshape(n)
+    x = np.stack([b[:, 0], b[:, 1], b[:, 0], b[:, 1]] * 2, axis=1)      # (n, 8)
+    y = np.stack([b[:, 2], b[:, 2], b[:, 3], b[:, 3]] * 2, axis=1)
+    z = np.stack([bot] * 4 + [top] * 4, axis=1)
+    ux, ix = np.unique(x, return_inverse=True)
+    uy, iy = np.unique(y, return_inverse=True)
+    uz, iz = np.unique(z, return_inverse=True)
+    key = (iz.reshape(-1).astype(np.int64) * len(uy) + iy.reshape(-1)) * len(ux) + ix.reshape(-1)
+    ukey, inv = np.unique(key, return_inverse=True)
+    kx = ukey % len(ux)
+    ky = (ukey // len(ux)) % len(uy)
+    kz = ukey // (len(ux) * len(uy))
+    nodes = np.ascontiguousarray(np.stack([ux[kx], uy[ky], uz[kz]], axis=1))
+    return nodes, np.ascontiguousarray(inv.reshape(n, 8).astype(np.int64))
+
+
+class BaseEquivalentSourceLayerSimulation(BasePFSimulation):
+    """
+    Equivalent-source layer: a 2D tensor / tree mesh plus the elevation of the top and bottom
+    face of every active cell (simpeg/potential_fields/base.py:411-474).  With ``engine="cuda"``
+    the layer's prisms go through the same device kernels as the 3D integral simulations.
+
+    Parameters
+    ----------
+    mesh : 2D mesh exposing ``dim``, ``n_cells`` and ``cell_bounds`` (n_cells, 4)
+    cell_z_top, cell_z_bottom : float or (n_active_cells,) array
+    """
+
+    def __init__(self, mesh, cell_z_top, cell_z_bottom, **kwargs):
+        super().__init__(mesh=mesh, **kwargs)
+        if isinstance(cell_z_top, (int, float)):
+            cell_z_top = float(cell_z_top) * np.ones(self.nC)
+        if isinstance(cell_z_bottom, (int, float)):
+            cell_z_bottom = float(cell_z_bottom) * np.ones(self.nC)
+        if (self.nC != len(cell_z_top)) | (self.nC != len(cell_z_bottom)):
+            raise AttributeError(
+                "'cell_z_top' and 'cell_z_bottom' must have length equal to number of",
+                "cells, and match the number of active cells.",
+            )
+        self._cell_z_top = np.asarray(cell_z_top, dtype=np.float64)
+        self._cell_z_bottom = np.asarray(cell_z_bottom, dtype=np.float64)
+
+    @property
+    def cell_z_top(self):
+        """Elevations for the top face of all cells in the layer."""
+        return self._cell_z_top
+
+    @property
+    def cell_z_bottom(self):
+        """Elevations for the bottom face of all cells in the layer."""
+        return self._cell_z_bottom
+
+    def _set_layer_mesh(self, value):
+        for attr in ("dim", "n_cells", "cell_bounds"):
+            if not hasattr(value, attr):
+                raise TypeError(f"mesh must be a 2D tensor or tree mesh (missing {attr!r})")
+        if value.dim != 2:
+            raise ValueError(
+                f"{type(self).__name__} mesh must be 2D, received a {value.dim}D mesh.")
+        self._mesh = value
+
+    mesh = property(BasePFSimulation.mesh.fget, _set_layer_mesh)
+
+    def _get_active_nodes(self):
+        if self._active_nodes_cache is None:
+            bounds = np.asarray(self.mesh.cell_bounds, dtype=np.float64)[self.active_cells]
+            self._active_nodes_cache = layer_nodes_and_cells(bounds, self.cell_z_top,
+                                                             self.cell_z_bottom)
+        return self._active_nodes_cache
+
+    def _tile_plan(self):
+        """A flat layer on a tensor mesh IS a one-cell-thick 3D tensor mesh (z-marching kernel);
+        anything else goes through the generic (nodes, cell_nodes) planner."""
+        from ..tiling import build_tile_plan, build_tile_plan_tensor
+
+        mesh, top, bot = self.mesh, self.cell_z_top, self.cell_z_bottom
+        flat = self.nC > 0 and np.all(top == top[0]) and np.all(bot == bot[0]) and bot[0] < top[0]
+        if flat and hasattr(mesh, "nodes_x") and hasattr(mesh, "nodes_y") \
+                and not hasattr(mesh, "total_nodes"):
+            xs = np.asarray(mesh.nodes_x, dtype=np.float64)
+            ys = np.asarray(mesh.nodes_y, dtype=np.float64)
+            if (len(xs) - 1) * (len(ys) - 1) == mesh.n_cells:
+                axes = (xs, ys, np.array([bot[0], top[0]]))
+                active = None if self.nC == mesh.n_cells else np.nonzero(self.active_cells)[0]
+                return build_tile_plan_tensor(axes, active, with_tiles=False)
+        return build_tile_plan(*self._get_active_nodes())

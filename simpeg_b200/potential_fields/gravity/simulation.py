@@ -15,7 +15,7 @@ import numpy as np
 from scipy.sparse.linalg import LinearOperator, aslinearoperator
 
 from ...utils import mkvc, sdiag
-from ..base import BasePFSimulation
+from ..base import BaseEquivalentSourceLayerSimulation, BasePFSimulation
 
 
 class Simulation3DIntegral(BasePFSimulation):
@@ -96,3 +96,27 @@ class Simulation3DIntegral(BasePFSimulation):
 
 
 __all__ = ["Simulation3DIntegral", "LinearOperator"]
+
+
+class SimulationEquivalentSourceLayer(BaseEquivalentSourceLayerSimulation, Simulation3DIntegral):
+    """
+    Equivalent-source layer gravity simulation with ``engine="cuda"`` -- mirror of
+    simpeg/potential_fields/gravity/simulation.py:727-939.
+
+    The reference evaluates ``choclo.prism.gravity_*`` per (receiver, cell) on the 8 vertices of
+    every prism (``gravity/_numba/_2d_mesh.py``); here the layer's prisms are handed to the same
+    device kernels as the 3D mesh (vertices shared where they coincide), with the same units:
+    ``G_newton * 1e8`` (mGal) / ``* 1e12`` (Eotvos) for densities in g/cc.
+
+    Parameters
+    ----------
+    mesh : 2D tensor or tree mesh (x, y discretisation of the layer)
+    cell_z_top, cell_z_bottom : float or (n_active_cells,) array
+    """
+
+    def __init__(self, mesh, cell_z_top, cell_z_bottom, engine="cuda", numba_parallel=True, **kwargs):
+        super().__init__(mesh, cell_z_top, cell_z_bottom, engine=engine,
+                         numba_parallel=numba_parallel, **kwargs)
+
+
+__all__ += ["SimulationEquivalentSourceLayer"]

@@ -3,4 +3,4 @@ from . import receivers, sources, survey, simulation  # noqa: F401
 from .receivers import Point  # noqa: F401
 from .sources import SourceField, UniformBackgroundField  # noqa: F401
 from .survey import Survey  # noqa: F401
-from .simulation import Simulation3DIntegral  # noqa: F401
+from .simulation import Simulation3DIntegral, SimulationEquivalentSourceLayer  # noqa: F401

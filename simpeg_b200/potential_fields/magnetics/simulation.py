@@ -16,7 +16,7 @@ import numpy as np
 from scipy.sparse.linalg import aslinearoperator
 
 from ...utils import dip_azimuth2cartesian, mkvc, sdiag, validate_string, validate_type
-from ..base import BasePFSimulation
+from ..base import BaseEquivalentSourceLayerSimulation, BasePFSimulation
 
 CUDA_SUPPORTED_COMPONENTS = {
     "tmi", "bx", "by", "bz", "bxx", "byy", "bzz", "bxy", "bxz", "byz", "tmi_x", "tmi_y", "tmi_z",
@@ -258,3 +258,25 @@ class Simulation3DIntegral(BasePFSimulation):
     def compute_amplitude(cls, b_xyz):
         """magnetics/simulation.py:557-565"""
         return np.linalg.norm(b_xyz.reshape((3, -1), order="F"), axis=0)
+
+
+class SimulationEquivalentSourceLayer(BaseEquivalentSourceLayerSimulation, Simulation3DIntegral):
+    """
+    Equivalent-source layer magnetic simulation with ``engine="cuda"`` -- mirror of
+    simpeg/potential_fields/magnetics/simulation.py:1235-1653.
+
+    The reference evaluates, per (receiver, cell), the kernels on the 8 vertices of the prism
+    (``magnetics/_numba/_2d_mesh.py``; ``choclo.prism.magnetic_field`` / ``magnetic_*`` divided by
+    mu_0 in the forward loops, ``1/(4 pi)`` times the kernel sums elsewhere -- the same number).
+    Here the prisms go through the device kernels of the 3D simulation; scalar / vector models,
+    components and column layout are those of :class:`Simulation3DIntegral`.
+
+    Parameters
+    ----------
+    mesh : 2D tensor or tree mesh (x, y discretisation of the layer)
+    cell_z_top, cell_z_bottom : float or (n_active_cells,) array
+    """
+
+    def __init__(self, mesh, cell_z_top, cell_z_bottom, engine="cuda", numba_parallel=True, **kwargs):
+        super().__init__(mesh, cell_z_top, cell_z_bottom, engine=engine,
+                         numba_parallel=numba_parallel, **kwargs)
