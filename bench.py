@@ -378,6 +378,35 @@ def run_cuda(args):
         }
         del sub, ws
 
+    # ---- device-resident Gauss-Newton CG: 5 iterations of
+    #      q = 2 G^T W^2 G p + beta p with all vectors in HBM, one all-reduce per iteration;
+    #      host vectors only for the gradient in and the step out (inside the timing) ---------
+    from simpeg_b200.gauss_newton import DeviceGaussNewtonCG
+
+    cg_iters = 5
+    jtj = sim.getJtJdiag(m_host)                          # stored-G column norms (not timed)
+    solver = DeviceGaussNewtonCG(sim, data_weights=np.ones(nD), reg_hessian=np.ones(nP),
+                                 beta=1e-3 * float(jtj.mean()), cg_maxiter=cg_iters, cg_rtol=0.0,
+                                 cg_atol=0.0)
+    solver.set_model(m_host)
+    solver.jacobi_preconditioner()                        # UpdatePreconditioner (cached diagonal)
+    g_host = rng.uniform(-1.0, 1.0, nP)
+    solver.find_search_direction(g_host)                  # warm-up
+    cg_t = []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        cg_step = solver.find_search_direction(g_host)
+        barrier()
+        cg_t.append(max_over_ranks(time.perf_counter() - t0))
+    cg_s = float(np.mean(cg_t))
+    cg = {"iterations": int(solver.cg_count), "ms_per_iteration": 1e3 * cg_s / max(solver.cg_count, 1),
+          "jvec_jtvec_gbs": 2 * g_bytes_total * solver.cg_count / cg_s / 1e9,
+          "rel_residual": float(solver.cg_rel_resid), "checksum": float(np.sum(cg_step)),
+          "what": "DeviceGaussNewtonCG.find_search_direction: gradient H2D, 5 x (gemv, row weights, "
+                  "gemv_t, all-reduce, fused vector kernels), step D2H; wall clock, max over ranks"}
+    del solver
+
     # ---- end to end through the public API, host buffers in and out -------------
     del sim, eng, x_dev, w_local, step, timers
     gc.collect()
@@ -462,6 +491,7 @@ def run_cuda(args):
                 "what": "new Simulation3DIntegral(engine='cuda') -> sim.G (tile plan on host, upload, "
                         "build) ; sim.Jvec / sim.Jtvec with numpy vectors in and out"},
         "gpu_launches": int(launches), "clocks": clocks, "other_sinks": extras,
+        "gauss_newton_cg": cg,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = {k: v for k, v in cpu_baseline(wl).items() if k != "seconds"}

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 3
+#define PF_ABI_VERSION 4
 
 typedef enum {
     PF_OK = 0,
@@ -255,6 +255,39 @@ int pf_plan_tensor_fill(int64_t nx, int64_t ny, int64_t nz, const double *xs, co
                         const int64_t *active, int64_t n_active, const uint8_t *used,
                         int64_t n_tiles, double *tile_xyz, uint16_t *tile_cell_nodes,
                         int32_t *tile_cell_col, int32_t *tile_n_nodes);
+
+/*
+ * Device-resident inner loop of the Gauss-Newton step: the vector algebra of
+ * ProjectedGNCG.findSearchDirection (simpeg/optimization.py:1625-1711) around the two products
+ * over G that make up L2DataMisfit.deriv2 (simpeg/data_misfit.py:341-343,
+ * 2 J^T W^T W J v).  All vectors have n = nP entries and stay on the device; the CG scalars
+ * live in `scal` (>= 4 doubles): scal[0] = sold, scal[1] = p.q, scal[2] = r.r, scal[3] = snew.
+ * Dot products are reduced in a fixed order (deterministic, identical on every rank).
+ *   pf_cg_init         step = 0; r = inactive * (-g); p = minv * r; scal[2] = r.r; scal[0] = r.p   (1638-1652)
+ *   pf_cg_hvp_combine  q = inactive * (scale * d * z + beta * R p); scal[1] = p.q                (1664)
+ *                      z = G^T W^2 G (d * p) (already summed over ranks); d = diagonal of the
+ *                      model-map derivative or NULL; R = regularisation Hessian as CSR
+ *                      (indptr, indices, values; int32) or diagonal `rdiag`, or both NULL
+ *   pf_cg_update       alpha = scal[0] / scal[1]; step += alpha p; r -= alpha q; h = minv * r;
+ *                      scal[2] = r.r; scal[3] = r.h                                              (1666-1676)
+ *   pf_cg_direction    p = h + (scal[3] / scal[0]) p; scal[0] = scal[3]                          (1678-1682)
+ *   pf_vec_mul         out = a * b (row weights W^2, chain rule with a diagonal derivative)
+ * `inactive` is one byte per entry (1 = free variable, 0 = on a bound) or NULL; `minv` is the
+ * diagonal of approxHinv (directives/_directives.py:2205-2233 UpdatePreconditioner) or NULL.
+ */
+int64_t pf_cg_workspace_bytes(int64_t n);
+int pf_cg_init(const double *g, const uint8_t *inactive, const double *minv, int64_t n,
+               double *step, double *r, double *p, double *scal, void *workspace,
+               int64_t workspace_bytes, void *stream);
+int pf_cg_hvp_combine(const double *z, const double *d, const double *p, const int32_t *indptr,
+                      const int32_t *indices, const double *values, const double *rdiag,
+                      double scale, double beta, const uint8_t *inactive, int64_t n, double *q,
+                      double *scal, void *workspace, int64_t workspace_bytes, void *stream);
+int pf_cg_update(const double *p, const double *q, const double *minv, int64_t n, double *step,
+                 double *r, double *h, double *scal, void *workspace, int64_t workspace_bytes,
+                 void *stream);
+int pf_cg_direction(const double *h, int64_t n, double *p, double *scal, void *stream);
+int pf_vec_mul(const double *a, const double *b, int64_t n, double *out, void *stream);
 
 /* FP64 pipe peak probe: runs a dependent-free DFMA loop and returns the
  * achieved FLOP/s (2 per DFMA) in *flops; used by bench.py for the roofline

@@ -15,7 +15,7 @@ import os
 LIB_PATH = Path(os.environ.get("PF_CUDA_LIB", Path(__file__).resolve().parent / "libpf_cuda.so"))
 
 PF_MAX_COMPONENTS = 16
-PF_ABI_VERSION = 3
+PF_ABI_VERSION = 4
 PF_F64, PF_F32 = 0, 1
 PF_GRAVITY, PF_MAGNETICS = 0, 1
 
@@ -45,6 +45,8 @@ EXPORTED_SYMBOLS = (
     "pf_amp_normalize", "pf_amp_combine", "pf_amp_spread",
     "pf_plan_tensor_count", "pf_plan_tensor_fill",
     "pf_probe_fp64_peak",
+    "pf_cg_workspace_bytes", "pf_cg_init", "pf_cg_hvp_combine", "pf_cg_update", "pf_cg_direction",
+    "pf_vec_mul",
 )
 
 
@@ -124,6 +126,12 @@ def load_library() -> ctypes.CDLL:
         "pf_plan_tensor_count": (i64, [i64] * 6 + [vp, i64, vp]),
         "pf_plan_tensor_fill": (i32, [i64] * 3 + [vp] * 3 + [i64] * 3 + [vp, i64, vp, i64] + [vp] * 4),
         "pf_probe_fp64_peak": (i32, [ctypes.POINTER(dbl), vp]),
+        "pf_cg_workspace_bytes": (i64, [i64]),
+        "pf_cg_init": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+        "pf_cg_hvp_combine": (i32, [vp] * 7 + [dbl, dbl, vp, i64, vp, vp, vp, i64, vp]),
+        "pf_cg_update": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+        "pf_cg_direction": (i32, [vp, i64, vp, vp, vp]),
+        "pf_vec_mul": (i32, [vp, vp, i64, vp, vp]),
     }
     for name, (restype, argtypes) in sigs.items():
         fn = getattr(lib, name)

@@ -50,6 +50,17 @@ def _worker(rank, world, port, out_dir):
             out[f"{store}_jvec"] = sim.Jvec(chi, v)
             out[f"{store}_jtvec"] = sim.Jtvec(chi, w)
             out[f"{store}_diag"] = sim.getJtJdiag(chi, W=sp.diags(wd))
+            if store == "ram":
+                # device-resident Gauss-Newton CG on the sharded G (one all-reduce per iteration)
+                from simpeg_b200.gauss_newton import DeviceGaussNewtonCG
+
+                scale = 1.0 / np.abs(out["ram_jtvec"]).max()
+                solver = DeviceGaussNewtonCG(sim, data_weights=wd * scale, reg_hessian=np.ones(chi.size),
+                                             beta=1e-2, cg_maxiter=6, cg_rtol=1e-8)
+                solver.set_model(chi)
+                out["ram_hvp"] = solver.hessian_vector(v)
+                out["ram_step"] = solver.find_search_direction(v - 0.5)
+                out["ram_cg_count"] = np.array(solver.cg_count)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), **out)
     finally:
         dist.destroy_process_group()
@@ -79,8 +90,17 @@ def test_two_rank_sharded_simulation(tmp_path):
     wd = rng.uniform(0.5, 1.5, size=sim.survey.nD)
     expected = {"dpred": G @ chi, "jvec": G @ v, "jtvec": G.T @ w,
                 "diag": np.einsum("i,ij,ij->j", wd**2, G, G)}
+    scale = 1.0 / np.abs(G.T @ w).max()
+    H = 2.0 * G.T @ (((wd * scale) ** 2)[:, None] * G) + 1e-2 * np.eye(chi.size)
+    from test_gpu_gauss_newton import reference_search_direction
+
+    step, count, _ = reference_search_direction(H, v - 0.5, chi, np.ones(chi.size), -np.inf, np.inf,
+                                                6, 1e-8, 0.0)
     for rank in range(world):
         z = np.load(tmp_path / f"r{rank}.npz")
+        assert vec_rel(z["ram_hvp"], H @ v) <= RTOL_NORMWISE
+        assert int(z["ram_cg_count"]) == count
+        assert vec_rel(z["ram_step"], step) <= 1e-7
         for store in ("ram", "forward_only"):
             for key, ref in expected.items():
                 assert vec_rel(z[f"{store}_{key}"], ref) <= RTOL_NORMWISE, (rank, store, key)
