@@ -289,6 +289,11 @@ int pf_cg_update(const double *p, const double *q, const double *minv, int64_t n
 int pf_cg_direction(const double *h, int64_t n, double *p, double *scal, void *stream);
 int pf_vec_mul(const double *a, const double *b, int64_t n, double *out, void *stream);
 
+/* Host staging copy (HOST pointers, a few threads): numpy vector <-> pinned staging buffer of the
+ * H2D / D2H transfers around the products (the boundary cost of SURVEY.md 8(b) "Callers across
+ * the boundary"). */
+int pf_host_copy(void *dst, const void *src, int64_t bytes);
+
 /* FP64 pipe peak probe: runs a dependent-free DFMA loop and returns the
  * achieved FLOP/s (2 per DFMA) in *flops; used by bench.py for the roofline
  * denominator of the compute-bound build kernels. */

@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = (
     "pf_plan_tensor_count", "pf_plan_tensor_fill",
     "pf_probe_fp64_peak",
     "pf_cg_workspace_bytes", "pf_cg_init", "pf_cg_hvp_combine", "pf_cg_update", "pf_cg_direction",
-    "pf_vec_mul",
+    "pf_vec_mul", "pf_host_copy",
 )
 
 
@@ -132,6 +132,7 @@ def load_library() -> ctypes.CDLL:
         "pf_cg_update": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
         "pf_cg_direction": (i32, [vp, i64, vp, vp, vp]),
         "pf_vec_mul": (i32, [vp, vp, i64, vp, vp]),
+        "pf_host_copy": (i32, [vp, vp, i64]),
     }
     for name, (restype, argtypes) in sigs.items():
         fn = getattr(lib, name)

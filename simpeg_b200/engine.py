@@ -186,7 +186,7 @@ class CudaEngine:
             raise ValueError(f"expected a vector of length {n}, got {a.shape[0]}")
         torch = self.torch
         i, pin = self._pinned(a.shape[0])
-        pin.numpy()[:] = a
+        self.lib.pf_host_copy(pin.data_ptr(), a.ctypes.data, a.nbytes)
         with torch.cuda.device(self.device):
             dev = torch.empty(a.shape[0], dtype=torch.float64, device=self.device)
             dev.copy_(pin, non_blocking=True)
@@ -207,7 +207,9 @@ class CudaEngine:
             ev = torch.cuda.Event()
             ev.record()
         ev.synchronize()
-        return pin.numpy().copy()
+        out = np.empty(t.numel(), dtype=np.float64)
+        self.lib.pf_host_copy(out.ctypes.data, pin.data_ptr(), out.nbytes)
+        return out
 
     def _jp(self, job):
         return ctypes.byref(self.plan), ctypes.byref(job)
@@ -370,6 +372,36 @@ class CudaEngine:
                                                 ws.data_ptr(), ws.numel() * 8, self._stream()),
                        "pf_colsumsq_amp")
         return d
+
+    def _alloc_G(self):
+        torch = self.torch
+        self.ld = -(-max(self.nP, 1) // _G_ALIGN) * _G_ALIGN
+        if self.G is None:
+            with torch.cuda.device(self.device):
+                self.G = torch.empty((self.n_rows, self.ld), dtype=self._g_torch, device=self.device)
+        return self.G
+
+    def G_row_chunks(self, max_bytes=256 << 20):
+        """Yield ``(start, stop, array)`` host copies of consecutive local rows of G."""
+        G = self._need_G()
+        item = 8 if self.g_dtype is np.float64 else 4
+        step = max(1, int(max_bytes // max(self.nP * item, 1)))
+        for a in range(0, self.n_rows, step):
+            b = min(a + step, self.n_rows)
+            yield a, b, G[a:b, : self.nP].cpu().numpy()
+
+    def load_G_rows(self, source, rows, max_bytes=256 << 20):
+        """Fill the local block of G from ``source[rows]`` (a host array / memmap of the FULL
+        matrix, ``rows`` = global index of every local row) instead of evaluating it."""
+        torch = self.torch
+        G = self._alloc_G()
+        item = 8 if self.g_dtype is np.float64 else 4
+        step = max(1, int(max_bytes // max(self.nP * item, 1)))
+        for a in range(0, self.n_rows, step):
+            b = min(a + step, self.n_rows)
+            block = np.ascontiguousarray(source[rows[a:b]], dtype=self.g_dtype)
+            G[a:b, : self.nP].copy_(torch.from_numpy(block))
+        return G
 
     def G_to_numpy(self):
         """Copy the local block of G to the host (small problems / tests only)."""

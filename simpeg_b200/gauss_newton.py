@@ -54,7 +54,8 @@ class DeviceGaussNewtonCG:
     def __init__(self, simulation, data_weights=None, reg_hessian=None, beta=0.0,
                  lower=-np.inf, upper=np.inf, cg_maxiter=5, cg_rtol=1e-3, cg_atol=0.0,
                  step_active_set=True, active_set_grad_scale=1e-2):
-        if getattr(simulation, "engine", None) != "cuda" or simulation.store_sensitivities != "ram":
+        if getattr(simulation, "engine", None) != "cuda" or simulation.store_sensitivities \
+                not in ("ram", "disk"):
             raise ValueError("DeviceGaussNewtonCG needs engine='cuda' and store_sensitivities='ram'")
         if getattr(simulation, "is_amplitude_data", False):
             raise NotImplementedError("amplitude data are not supported by the device CG loop")
@@ -72,7 +73,7 @@ class DeviceGaussNewtonCG:
         self.step_active_set = bool(step_active_set)
         self.active_set_grad_scale = float(active_set_grad_scale)
         self.cg_count, self.cg_abs_resid, self.cg_rel_resid = 0, np.inf, np.inf
-        self.approxHinv = None
+        self._approx_hinv = self._minv_t = None
         torch, dev = self.torch, self.engine.device
 
         w = np.ones(self.nD) if data_weights is None else np.asarray(data_weights, dtype=np.float64)
@@ -86,6 +87,16 @@ class DeviceGaussNewtonCG:
         self._deriv_t = None
         self._scal = torch.zeros(8, dtype=torch.float64, device=dev)
         self._ws = torch.empty(self.lib.pf_cg_workspace_bytes(0) // 8, dtype=torch.float64, device=dev)
+
+    @property
+    def approxHinv(self):
+        """Diagonal of the preconditioner (``opt.approxHinv`` of the reference), or None."""
+        return self._approx_hinv
+
+    @approxHinv.setter
+    def approxHinv(self, value):
+        self._approx_hinv = None if value is None else np.asarray(value, dtype=np.float64).reshape(-1)
+        self._minv_t = None                   # uploaded once, at the next solve
 
     # ------------------------------------------------------------------ set-up
     def _ptr(self, t):
@@ -217,7 +228,9 @@ class DeviceGaussNewtonCG:
             stream = eng._stream()
             g_t = eng.to_device(g)
             mask = None if inactive.all() else torch.from_numpy(inactive.astype(np.uint8)).to(eng.device)
-            minv = None if self.approxHinv is None else eng.to_device(self.approxHinv, n=n)
+            if self._approx_hinv is not None and self._minv_t is None:
+                self._minv_t = eng.to_device(self._approx_hinv, n=n)
+            minv = self._minv_t
             step, r, p, q, h = (torch.empty(n, dtype=torch.float64, device=eng.device) for _ in range(5))
             scal = self._scal
             _lib.check(lib.pf_cg_init(g_t.data_ptr(), self._ptr(mask), self._ptr(minv), n, step.data_ptr(),

@@ -3,7 +3,8 @@
 simpeg/potential_fields/base.py:24-408 for the integral-equation hot path.
 
 Kept from the reference: constructor keywords, ``store_sensitivities``
-('ram' / 'forward_only'; 'disk' is rejected for this engine),
+('ram' / 'forward_only' / 'disk': built on the GPU, kept in HBM and also written to
+``sensitivity_path`` in the reference's memmap layout),
 ``sensitivity_dtype`` (forced to float64 when ``forward_only``,
 base.py:196-215), ``engine`` validation with the reference's error text
 (base.py:241-256), ``_get_active_nodes`` (base.py:371-399, cached here) and
@@ -154,10 +155,6 @@ class BasePFSimulation:
         self.survey = survey
         self.sensitivity_path = sensitivity_path
         self.n_processes = n_processes
-        if self.store_sensitivities == "disk":
-            raise NotImplementedError(
-                "store_sensitivities='disk' is not available with engine='cuda' "
-                "(use 'ram' or 'forward_only').")
         n_cells = mesh.n_cells
         if active_cells is None:
             active_cells = np.ones(n_cells, dtype=bool)
@@ -384,8 +381,48 @@ class BasePFSimulation:
         return self._ops.forward(model)
 
     def _sensitivity_matrix(self):
-        """Build the local block of G on the device (gravity/simulation.py:585-629)."""
-        return self._dev.build_G()
+        """Build the local block of G on the device (gravity/simulation.py:585-629).  With
+        ``store_sensitivities="disk"`` the matrix is also written to ``sensitivity_path`` in the
+        reference's format (lines 599-606: a raw row-major ``np.memmap`` of ``sensitivity_dtype``,
+        shape ``(nD, nP)``); products keep using the copy in HBM."""
+        G = self._dev.build_G()
+        if self.store_sensitivities == "disk":
+            self._write_sensitivities()
+        return G
+
+    def _write_sensitivities(self):
+        """Every rank writes its rows into the one file (rank 0 creates it)."""
+        ops = self._ops
+        coll, rows = ops.coll, ops.sharding.local_rows
+        shape = (self.survey.nD, self._n_columns())
+        if coll.rank == 0:
+            np.memmap(self.sensitivity_path, shape=shape, dtype=self.sensitivity_dtype, order="C",
+                      mode="w+").flush()
+        coll.barrier()
+        out = np.memmap(self.sensitivity_path, shape=shape, dtype=self.sensitivity_dtype, order="C",
+                        mode="r+")
+        for a, b, block in ops.engine.G_row_chunks():
+            out[rows[a:b]] = block
+        out.flush()
+        del out
+        coll.barrier()
+
+    def load_sensitivities(self, path=None):
+        """
+        Use a sensitivity matrix that is already on disk -- written by this engine or by the
+        reference with ``store_sensitivities="disk"`` (gravity/simulation.py:599-606, same raw
+        layout) -- instead of evaluating it: every rank uploads its rows to HBM.
+        """
+        path = self.sensitivity_path if path is None else path
+        shape = (self.survey.nD, self._n_columns())
+        source = np.memmap(path, shape=shape, dtype=self.sensitivity_dtype, order="C", mode="r")
+        ops = self._ops
+        ops.engine.load_G_rows(source, ops.sharding.local_rows)
+        del source
+        if hasattr(self, "_G"):
+            del self._G
+        self._G_loaded = True
+        return self.G
 
     def _sensitivity_matrix_transpose_dot_vec(self, vector):
         """G.T @ v without storing G (gravity/simulation.py:631-671)."""
@@ -414,7 +451,8 @@ class BasePFSimulation:
             if self.store_sensitivities == "forward_only":
                 self._G = self._sensitivity_matrix_as_operator()
             else:
-                self._sensitivity_matrix()
+                if not getattr(self, "_G_loaded", False):
+                    self._sensitivity_matrix()
                 ops = self._ops
                 shape = (self.survey.nD, self._n_columns())
                 self._G = DeviceLinearOperator(shape, ops.gemv, ops.gemv_t, ops.G_to_numpy)

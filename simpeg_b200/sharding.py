@@ -117,6 +117,10 @@ class Collectives:
         if self.world_size == 1:
             self._dist = None
 
+    def barrier(self):
+        if self._dist is not None:
+            self._dist.barrier(group=self.group)
+
     def all_reduce_sum(self, tensor):
         """In-place sum over ranks of a partial (nP,) vector (Jtvec, JtJ diagonal)."""
         if self._dist is not None:

@@ -121,3 +121,39 @@ def test_receivers_inside_below_and_beside_the_mesh(physics, comps, mt):
         v = rng.uniform(size=eng.n_rows)
         assert vec_rel(eng.to_host(eng.forward_dev(eng.to_device(m))), G @ m) <= RTOL_NORMWISE
         assert vec_rel(eng.to_host(eng.gt_dot_v_dev(eng.to_device(v))), G.T @ v) <= RTOL_NORMWISE
+
+
+def test_store_sensitivities_disk_roundtrip(tmp_path):
+    """store_sensitivities='disk' (gravity/simulation.py:599-606): G is built on the GPU and also
+    written as the reference's raw row-major memmap; load_sensitivities() of a second simulation
+    -- or of a file the reference wrote -- uploads it instead of evaluating it."""
+    from helpers import RTOL_NORMWISE, load_golden, vec_rel
+    from sim_fixtures import gravity_survey, small_mesh
+    from simpeg_b200 import maps
+    from simpeg_b200.potential_fields import gravity
+
+    mesh = small_mesh()
+    path = str(tmp_path / "sens.bin")
+    kw = dict(survey=gravity_survey(["gz", "gzz"]), rhoMap=maps.IdentityMap(nP=mesh.n_cells),
+              sensitivity_dtype=np.float64, sensitivity_path=path)
+    sim = gravity.Simulation3DIntegral(mesh, store_sensitivities="disk", **kw)
+    rho = np.random.default_rng(0).uniform(-0.5, 0.5, mesh.n_cells)
+    d = sim.dpred(rho)
+    G = sim.G.to_numpy()
+    on_disk = np.memmap(path, dtype=np.float64, mode="r", shape=G.shape, order="C")
+    assert np.array_equal(np.asarray(on_disk), G)
+    # a second simulation reads the file; make sure it does not evaluate anything
+    sim2 = gravity.Simulation3DIntegral(mesh, store_sensitivities="ram", **kw)
+    sim2._sensitivity_matrix = None          # calling it would raise
+    sim2.load_sensitivities()
+    assert np.array_equal(sim2.dpred(rho), d)
+    assert np.array_equal(sim2.G.to_numpy(), G)
+    # float32 file as the reference writes it by default (base.py:86)
+    path32 = str(tmp_path / "sens32.bin")
+    ref32 = np.memmap(path32, dtype=np.float32, mode="w+", shape=G.shape, order="C")
+    ref32[:] = G.astype(np.float32)
+    ref32.flush()
+    kw32 = dict(kw, sensitivity_dtype=np.float32, sensitivity_path=path32)
+    sim3 = gravity.Simulation3DIntegral(mesh, store_sensitivities="ram", **kw32)
+    sim3.load_sensitivities()
+    assert vec_rel(sim3.dpred(rho), G @ rho) <= 1e-6

@@ -61,6 +61,13 @@ def _worker(rank, world, port, out_dir):
                 out["ram_hvp"] = solver.hessian_vector(v)
                 out["ram_step"] = solver.find_search_direction(v - 0.5)
                 out["ram_cg_count"] = np.array(solver.cg_count)
+        # store_sensitivities="disk": both ranks write their rows into ONE reference-format file
+        sim = magnetics.Simulation3DIntegral(
+            mesh, survey=magnetic_survey(["tmi", "bx"], two_objects=True),
+            chiMap=make_mapping("identity_map", 3 * mesh.n_cells), model_type="vector",
+            store_sensitivities="disk", sensitivity_dtype=np.float64, engine="cuda",
+            sensitivity_path=os.path.join(out_dir, "sens.bin"))
+        out["disk_dpred"] = sim.dpred(chi)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), **out)
     finally:
         dist.destroy_process_group()
@@ -90,6 +97,10 @@ def test_two_rank_sharded_simulation(tmp_path):
     wd = rng.uniform(0.5, 1.5, size=sim.survey.nD)
     expected = {"dpred": G @ chi, "jvec": G @ v, "jtvec": G.T @ w,
                 "diag": np.einsum("i,ij,ij->j", wd**2, G, G)}
+    from helpers import rowwise_rel
+
+    on_disk = np.memmap(tmp_path / "sens.bin", dtype=np.float64, mode="r", shape=G.shape, order="C")
+    assert rowwise_rel(np.asarray(on_disk), G).max() <= RTOL_NORMWISE
     scale = 1.0 / np.abs(G.T @ w).max()
     H = 2.0 * G.T @ (((wd * scale) ** 2)[:, None] * G) + 1e-2 * np.eye(chi.size)
     from test_gpu_gauss_newton import reference_search_direction
@@ -99,6 +110,7 @@ def test_two_rank_sharded_simulation(tmp_path):
     for rank in range(world):
         z = np.load(tmp_path / f"r{rank}.npz")
         assert vec_rel(z["ram_hvp"], H @ v) <= RTOL_NORMWISE
+        assert vec_rel(z["disk_dpred"], G @ chi) <= RTOL_NORMWISE
         assert int(z["ram_cg_count"]) == count
         assert vec_rel(z["ram_step"], step) <= 1e-7
         for store in ("ram", "forward_only"):

@@ -39,9 +39,11 @@ def test_sensitivity_dtype_defaults():
     assert sim.sensitivity_dtype is np.float64
 
 
-def test_disk_not_available_and_bad_store():
-    with pytest.raises(NotImplementedError, match="disk"):
-        gravity.Simulation3DIntegral(small_mesh(), store_sensitivities="disk")
+def test_store_sensitivities_values():
+    # base.py:170-190: 'disk', 'ram', 'forward_only'
+    sim = gravity.Simulation3DIntegral(small_mesh(), store_sensitivities="disk",
+                                       sensitivity_path="/tmp/unused")
+    assert sim.store_sensitivities == "disk" and sim.sensitivity_path == "/tmp/unused"
     with pytest.raises(ValueError, match="store_sensitivities"):
         gravity.Simulation3DIntegral(small_mesh(), store_sensitivities="tape")
 
