@@ -141,10 +141,22 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
     const double r = sqrt(e * e + n * n + u * u);
     if (FAM == 12) {
         double Aee = 0, Ann = 0, Auu = 0, Len = 0, Leu = 0, Lnu = 0;
+        constexpr int NEED_ALL = NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU;
+#if !defined(PF_NO_ATAN_IDENTITY) && !defined(PF_NO_LOCKSTEP)
+        const bool lockstep = (need == NEED_ALL);
+#else
+        const bool lockstep = false;
+#endif
+        if (lockstep) {
+            // all six primitives: two atans + three logs in lock-step (pf_math.cuh), third atan
+            // from the identity below
+            pf_node_atan2_log3(e, n, u, r, Aee, Ann, Len, Leu, Lnu);
+            need = NEED_AUU;
+        }
         if (need & NEED_AEE) Aee = pf_safe_atan2(n * u, e * r);
         if (need & NEED_ANN) Ann = pf_safe_atan2(e * u, n * r);
 #ifndef PF_NO_ATAN_IDENTITY
-        if ((need & (NEED_AEE | NEED_ANN | NEED_AUU)) == (NEED_AEE | NEED_ANN | NEED_AUU)) {
+        if (lockstep || (need & (NEED_AEE | NEED_ANN | NEED_AUU)) == (NEED_AEE | NEED_ANN | NEED_AUU)) {
             // The three arguments a = nu/(er), b = eu/(nr), c = en/(ur) share the sign of
             // e n u and satisfy ab + bc + ca = 1, hence atan a + atan b + atan c = +-pi/2;
             // with exactly one zero coordinate the sum is +-pi/2 by the sign of the other
@@ -215,7 +227,8 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         }
         return;
     }
-    eval_raw<FAM>(p.need, e, n, u, k);
+    eval_raw<FAM>((PROG == PROG_ALL6) ? (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU) : p.need,
+                  e, n, u, k);
     // raw planes: straight-line predicated stores (no descriptor loop)
     {
         const int rm = p.raw_mask;   // raw planes occupy slots 0.. in increasing q (host guarantees it)
@@ -531,6 +544,45 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 }
             }
             double fsum = 0.0;
+            if constexpr (PF_IS_TMI(PROG)) {
+                // one component, PROG outputs = planes = column blocks (block o at o * nC), one
+                // factor: slot-major, all addresses of a slot derived once (immediate offsets)
+                constexpr int NO = PROG;
+                const double factor = s_fac[0];
+                const unsigned long long dst0 = s_dst[0];
+                const int64_t blk_bytes = nC * (int64_t)((SINK == SINK_STORE) ? sizeof(GT) : sizeof(double));
+#pragma unroll
+                for (int s = 0; s < NR; ++s) {
+                    if (cbase[s] < 0) continue;
+                    const char *q = pl + o00[s];
+                    double *dp = dprev + tid + s * PF_THREADS;
+                    const bool st = col[s] >= 0;
+                    const char *gp = reinterpret_cast<const char *>(dst0)
+                                     + (int64_t)(unsigned)col[s] * (int64_t)((SINK == SINK_STORE) ? sizeof(GT) : sizeof(double));
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) {
+                        const char *qq = q + o * LAYER_BYTES;
+                        const double d_new = *reinterpret_cast<const double *>(qq)
+                                             - *reinterpret_cast<const double *>(qq + 8)
+                                             - *reinterpret_cast<const double *>(qq + sW)
+                                             + *reinterpret_cast<const double *>(qq + sW + 8);
+                        const double d_old = dp[o * (NR * PF_THREADS)];
+                        dp[o * (NR * PF_THREADS)] = d_new;
+                        const double g = factor * (d_new - d_old);
+                        if (st) {
+                            if (SINK == SINK_STORE)
+                                *reinterpret_cast<GT *>(const_cast<char *>(gp) + o * blk_bytes) = (GT)g;
+                            else
+                                fsum += g * __ldg(reinterpret_cast<const double *>(gp + o * blk_bytes));
+                        }
+                    }
+                }
+                if (SINK == SINK_FORWARD && emit) {
+                    fsum = warp_sum(fsum);
+                    if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd] += fsum;
+                }
+                return;
+            }
 #define PF_PHASE2_BODY(O, POFF)                                                                   \
             {                                                                                     \
                 GT *grow = reinterpret_cast<GT *>(s_dst[O]);                                      \
@@ -1013,7 +1065,13 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
         passes[i].prog = PROG_GENERIC;
         if (passes[i].family == 12 && job->physics == PF_MAGNETICS && p.n_fwd == 1 &&
             job->components[p.outs[0].ci] == PF_TMI)
-            passes[i].prog = (p.nblk == 3) ? PROG_TMI_VECTOR : PROG_TMI_SCALAR;
+        {
+            // the TMI programs assume output o = plane o = column block o with one common factor
+            bool regular = p.direct && p.n_out == p.nblk;
+            for (int o = 0; o < p.n_out && regular; ++o)
+                regular = p.outs[o].blk == o && p.outs[o].factor == p.outs[0].factor;
+            if (regular) passes[i].prog = (p.nblk == 3) ? PROG_TMI_VECTOR : PROG_TMI_SCALAR;
+        }
         else if (passes[i].family == 12 &&
                  p.need == (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU))
             passes[i].prog = PROG_ALL6;
