@@ -468,9 +468,9 @@ def run_cuda(args):
             "kernel": "pf_march_kernel<12, PROG_TMI_VECTOR, SINK_STORE, double, 4> (G build)", "bound": "fp64",
             "achieved": build_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
             "frac": build_tflops / (fp64_peak / 1e12),
-            # ncu (profiles/r1f_build_products_summary.md): 7.123 GB written + 0.090 GB read for a
-            # 7.104 GB block of G -> DRAM bytes per launch = 1.0154 x the block it writes
-            "traffic": 1.0154 * g_bytes_local,
+            # ncu (profiles/r1g_kernels_summary.md): 7.135 GB written + 0.099 GB read for a
+            # 7.104 GB block of G -> DRAM bytes per launch = 1.0183 x the block it writes
+            "traffic": 1.0183 * g_bytes_local,
             "note": f"algorithmic flop-eq/pair = 339*nN/nC + 64 = {flop_eq_per_pair:.1f} (SURVEY 8(d)); "
                     "peak = DFMA probe measured in this run (pf_probe_fp64_peak); per GPU; "
                     "ncu: FP64 pipe 58-64 % busy (the kernel issues ~260 FP64 instructions per pair)",

@@ -15,3 +15,8 @@ ncu --set full --clock-control none --import-source on -k regex:'gemv_kernel|col
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
 tail -c 600 gpurun_out/bench_${TAG}.json
+# 4) fp32-stored G products and the draped equivalent-source layer (tile kernel)
+ncu --set full --clock-control none --import-source on -k regex:'gemv_kernel|column_kernel' -c 2 \
+    -o gpurun_out/prof_f32_${TAG} python scripts/prof_f32.py > gpurun_out/prof_f32_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'pf_tile_kernel' -c 1 \
+    -o gpurun_out/prof_layer_${TAG} python scripts/prof_layer.py > gpurun_out/prof_layer_${TAG}.log 2>&1
