@@ -274,6 +274,18 @@ class BasePFSimulation:
         return d if sp.issparse(d) else sp.csr_matrix(d)
 
     @staticmethod
+    def _jtj_diagonal(gtg_diagonal, deriv):
+        """``((sdiag(sqrt(gtg)) @ deriv).power(2)).sum(axis=0)`` (gravity/simulation.py:279-283):
+        diag(J^T W^T W J) from diag(G^T W^T W G) and the model-map derivative.  An identity
+        derivative returns the diagonal itself (the sparse products cost more than the 98 GB
+        column sums they follow)."""
+        if getattr(deriv, "is_identity", False):
+            return np.array(gtg_diagonal, dtype=np.float64)
+        from ..utils import mkvc, sdiag
+
+        return mkvc((sdiag(np.sqrt(gtg_diagonal)) @ deriv).power(2).sum(axis=0))
+
+    @staticmethod
     def _deriv_dot(deriv, v):
         """deriv @ v, skipping the sparse product for an identity mapping."""
         if getattr(deriv, "is_identity", False):

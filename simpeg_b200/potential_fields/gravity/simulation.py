@@ -14,7 +14,6 @@ import hashlib
 import numpy as np
 from scipy.sparse.linalg import LinearOperator, aslinearoperator
 
-from ...utils import mkvc, sdiag
 from ..base import BaseEquivalentSourceLayerSimulation, BasePFSimulation
 
 
@@ -66,7 +65,7 @@ class Simulation3DIntegral(BasePFSimulation):
         if not use_cached:
             self._gtg_diagonal = self._get_gtg_diagonal(weights)
             self._weights_sha256 = weights_sha256
-        diagonal = mkvc((sdiag(np.sqrt(self._gtg_diagonal)) @ self.rhoDeriv).power(2).sum(axis=0))
+        diagonal = self._jtj_diagonal(self._gtg_diagonal, self.rhoDeriv)
         return diagonal
 
     def _get_gtg_diagonal(self, weights):

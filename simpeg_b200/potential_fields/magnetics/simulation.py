@@ -152,7 +152,7 @@ class Simulation3DIntegral(BasePFSimulation):
         if not use_cached:
             self._gtg_diagonal = self._get_gtg_diagonal(weights)
             self._weights_sha256 = weights_sha256
-        diagonal = mkvc((sdiag(np.sqrt(self._gtg_diagonal)) @ self.chiDeriv).power(2).sum(axis=0))
+        diagonal = self._jtj_diagonal(self._gtg_diagonal, self.chiDeriv)
         return diagonal
 
     def _get_gtg_diagonal(self, weights):
