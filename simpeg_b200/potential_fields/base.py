@@ -332,7 +332,27 @@ class BasePFSimulation:
         if axes is not None:
             active = None if self.nC == self.mesh.n_cells else np.nonzero(self.active_cells)[0]
             return build_tile_plan_tensor(axes, active, with_tiles=False)
-        return build_tile_plan(*self._get_active_nodes())
+        return self._cached_generic_plan(lambda: build_tile_plan(*self._get_active_nodes()))
+
+    def _cached_generic_plan(self, build):
+        """The generic (nodes, cell_nodes) planner costs seconds per million cells and depends only
+        on the mesh and the active cells: keep its result on the mesh object, so that further
+        simulations on the same mesh (other surveys, components, store modes) reuse it."""
+        import hashlib
+
+        key = hashlib.sha1(np.packbits(self.active_cells).tobytes()).hexdigest()
+        key += "|" + getattr(self, "_plan_cache_tag", "")
+        cache = getattr(self.mesh, "_pf_tile_plans", None)
+        if cache is None:
+            cache = {}
+            try:
+                self.mesh._pf_tile_plans = cache
+            except (AttributeError, TypeError):       # meshes that refuse new attributes
+                pass
+        if key not in cache:
+            cache.clear()                              # one plan per mesh is enough
+            cache[key] = build()
+        return cache[key]
 
     def _get_components_and_receivers(self):
         """base.py:401-408"""
@@ -583,4 +603,8 @@ class BaseEquivalentSourceLayerSimulation(BasePFSimulation):
                 axes = (xs, ys, np.array([bot[0], top[0]]))
                 active = None if self.nC == mesh.n_cells else np.nonzero(self.active_cells)[0]
                 return build_tile_plan_tensor(axes, active, with_tiles=False)
-        return build_tile_plan(*self._get_active_nodes())
+        import hashlib
+
+        self._plan_cache_tag = "layer:" + hashlib.sha1(
+            np.ascontiguousarray(top).tobytes() + np.ascontiguousarray(bot).tobytes()).hexdigest()
+        return self._cached_generic_plan(lambda: build_tile_plan(*self._get_active_nodes()))

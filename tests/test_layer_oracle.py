@@ -115,3 +115,17 @@ def test_layer_helper_builds_simulations():
     case = load_layer_golden(LAYER_GOLDEN[0])
     sim = layer_simulation(case)
     assert sim.survey.nD == case["G"].shape[0]
+
+
+def test_generic_tile_plan_is_cached_on_the_mesh():
+    mesh2 = CellBoundsMesh2D(TensorMesh([np.full(12, 2.0), np.full(9, 5.0)], "CC").cell_bounds)
+    top = -1.0 - np.linspace(0, 1, mesh2.n_cells)
+    a = gravity.SimulationEquivalentSourceLayer(mesh2, top, -4.0)
+    b = magnetics.SimulationEquivalentSourceLayer(mesh2, top, -4.0)
+    assert a._tile_plan() is b._tile_plan()            # same mesh, cells and faces: planned once
+    c = gravity.SimulationEquivalentSourceLayer(mesh2, top - 0.5, -4.0)
+    assert c._tile_plan() is not a._tile_plan()        # different prisms: new plan
+    active = np.ones(mesh2.n_cells, dtype=bool)
+    active[::3] = False
+    d = gravity.SimulationEquivalentSourceLayer(mesh2, top[active], -4.0, active_cells=active)
+    assert d._tile_plan().n_cells == int(active.sum())
