@@ -55,3 +55,21 @@ def test_argument_errors_are_status_codes():
     assert lib.pf_build_G(ctypes.byref(plan), ctypes.byref(job), None, 0, 0, None) == 0
     assert lib.pf_gemv(None, 0, 0, 0, 0, None, None, None, 0, None) == 0
     assert lib.pf_gemv(None, 4, 4, 2, 0, None, None, None, 0, None) == -1
+
+
+def test_host_staging_copy_and_cg_argument_checks():
+    import numpy as np
+
+    lib = _lib.load_library()
+    # pf_host_copy is a host-only entry point: usable without a GPU
+    for n in (0, 7, 131072, 3_000_001):
+        src = np.random.default_rng(n).uniform(size=n)
+        dst = np.full(n, -1.0)
+        assert lib.pf_host_copy(dst.ctypes.data, src.ctypes.data, src.nbytes) == 0
+        assert np.array_equal(src, dst)
+    assert lib.pf_host_copy(None, None, 16) == -1
+    # the CG entry points validate before touching the device
+    assert lib.pf_cg_workspace_bytes(10) > 0
+    assert lib.pf_cg_init(None, None, None, 5, None, None, None, None, None, 0, None) == -1
+    assert lib.pf_vec_mul(None, None, 0, None, None) == 0
+    assert lib.pf_vec_mul(None, None, 3, None, None) == -1
