@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = (
     "pf_plan_tensor_count", "pf_plan_tensor_fill",
     "pf_probe_fp64_peak",
     "pf_cg_workspace_bytes", "pf_cg_init", "pf_cg_hvp_combine", "pf_cg_update", "pf_cg_direction",
-    "pf_vec_mul", "pf_host_copy",
+    "pf_vec_mul", "pf_host_copy", "pf_math_probe",
 )
 
 
@@ -133,6 +133,7 @@ def load_library() -> ctypes.CDLL:
         "pf_cg_direction": (i32, [vp, i64, vp, vp, vp]),
         "pf_vec_mul": (i32, [vp, vp, i64, vp, vp]),
         "pf_host_copy": (i32, [vp, vp, i64]),
+        "pf_math_probe": (i32, [i32, vp, vp, vp, vp, i64, vp]),
     }
     for name, (restype, argtypes) in sigs.items():
         fn = getattr(lib, name)

@@ -9,6 +9,7 @@
 //   magnetics/simulation.py:252,489 (G @ x), 533 (G.T @ v), 441-456 (einsum,
 //   amplitude row loop), 491-495, 529-565 (amplitude algebra).
 #include "pf_common.cuh"
+#include "pf_math.cuh"
 
 namespace {
 
@@ -591,5 +592,39 @@ extern "C" int pf_probe_fp64_peak(double *flops, void *stream_)
     cudaFree(sink);
     const double n_fma = (double)blocks * 256.0 * PROBE_CHAINS * PROBE_ITERS;
     *flops = 2.0 * n_fma / (best_ms * 1e-3);
+    return PF_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Element-wise probe of the branch-free fp64 building blocks of pf_math.cuh (tests only):
+// kind 0 = pf_div(a, b), 1 = pf_atan_ratio(a, b) = atan(a / b), 2 = pf_log_ratio(a, b) = log(a / b),
+// 3 = pf_safe_log(a, b, c) with r = sqrt(a^2 + b^2 + c^2).
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) math_probe_kernel(int kind, const double *a, const double *b,
+                                                         const double *c, double *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v;
+    if (kind == 0) v = pf_div(a[i], b[i]);
+    else if (kind == 1) v = pf_atan_ratio(a[i], b[i]);
+    else if (kind == 2) v = pf_log_ratio(a[i], b[i]);
+    else v = pf_safe_log(a[i], b[i], c[i], sqrt(a[i] * a[i] + b[i] * b[i] + c[i] * c[i]));
+    out[i] = v;
+}
+}  // namespace
+
+extern "C" int pf_math_probe(int kind, const double *a, const double *b, const double *c, double *out,
+                             int64_t n, void *stream)
+{
+    PF_CHECK_ARG(kind >= 0 && kind <= 3, "bad kind");
+    PF_CHECK_ARG(n >= 0, "negative length");
+    if (n == 0) return PF_OK;
+    PF_CHECK_ARG(a && b && out && (kind != 3 || c), "null vector");
+    math_probe_kernel<<<(unsigned)pf_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(kind, a, b, c, out, n);
+    PF_COUNT_LAUNCH();
+    PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
 }
