@@ -83,7 +83,7 @@ struct LaunchParams {
     int direct;        // outs[o].plane == o for every o (phase 2 can unroll with constant offsets)
     int raw_mask;      // raw kernels stored as planes: bit q set -> slot = rank of q among the set bits
     int n_combo;       // planes [n_planes - n_combo, n_planes) are DOT3 / QUAD combinations
-    int pad;
+    int n_buf;         // marching kernel: 2 = node planes double-buffered (one barrier per layer), 1 = single
     PlaneDesc planes[MAX_PLANES];
     OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
@@ -459,8 +459,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const int n_planes = p.n_planes;
     const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
     const int buf_doubles = n_planes * NCAP;
-    constexpr int N_BUF = 2;
-    double *dprev = smem + N_BUF * (size_t)buf_doubles;       // [n_out][NR][THREADS] corner differences
+    const int n_buf = p.n_buf;    // 1 when two buffers would not leave room for 3 CTAs per SM
+    double *dprev = smem + n_buf * (size_t)buf_doubles;       // [n_out][NR][THREADS] corner differences
     double *wacc = dprev + (size_t)n_out * NR * PF_THREADS;   // [WARPS][n_fwd] (forward)
     // per-output bookkeeping, refreshed once per receiver: destination of column 0 of
     // the output's row/block (store) or of its model block (forward), and its factor
@@ -633,10 +633,11 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
 
         // node layers iz_begin .. iz_end; the cells between layers L-1 and L are emitted at L
         for (int L = iz_begin; L <= iz_end; ++L) {
-            double *planes = smem + (L & 1) * buf_doubles;
+            double *planes = smem + ((n_buf == 2) ? (L & 1) * buf_doubles : 0);
             phase1(L, planes);
             __syncthreads();
             phase2(L, planes);
+            if (n_buf == 1) __syncthreads();
         }
         __syncthreads();   // all warps done with the last layer (buffers, dprev and wacc are reused)
         if (SINK == SINK_FORWARD) {
@@ -1127,11 +1128,25 @@ int launch_pass(const Pass &pass, cudaStream_t stream)
 // ---- z-marching kernel dispatch (tensor meshes) --------------------------------
 constexpr size_t MARCH_SMEM_LIMIT = 110 * 1024;  // keeps >= 2 CTAs per SM
 
+size_t march_smem_n(const LaunchParams &p, int nr, bool forward, int n_buf)
+{
+    return (((size_t)n_buf * p.n_planes + p.n_out) * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0))
+           * sizeof(double);
+}
+
+// double-buffered node planes (one barrier per layer) unless that costs the third CTA per SM and
+// a single buffer (two barriers per layer) keeps it
+constexpr size_t MARCH_SMEM_3CTAS = 74 * 1024;
+int march_buffers(const LaunchParams &p, int nr, bool forward)
+{
+    if (march_smem_n(p, nr, forward, 2) > MARCH_SMEM_3CTAS && march_smem_n(p, nr, forward, 1) <= MARCH_SMEM_3CTAS)
+        return 1;
+    return 2;
+}
+
 size_t march_smem(const LaunchParams &p, int nr, bool forward)
 {
-    const size_t n_buf = 2;
-    return ((n_buf * (size_t)p.n_planes + p.n_out) * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0))
-           * sizeof(double);
+    return march_smem_n(p, nr, forward, march_buffers(p, nr, forward));
 }
 
 // node rounds per layer (4 -> 1024-node footprints, 2 -> 512) or 0 when the pass
@@ -1149,12 +1164,14 @@ int launch_march_kernel(const LaunchParams &p, cudaStream_t stream)
 {
     const size_t smem = march_smem(p, NR, SINK == SINK_FORWARD);
     auto kernel = pf_march_kernel<FAM, PROG, SINK, GT, NR>;
+    LaunchParams q = p;
+    q.n_buf = march_buffers(p, NR, SINK == SINK_FORWARD);
     PF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunks = pf_ceil_div(p.n_receivers, p.rc);
     PF_CHECK_ARG(chunks <= 65535, "too many receiver chunks");
     const int n_fp = (NR == 4) ? p.plan.n_footprints4 : p.plan.n_footprints2;
     dim3 grid((unsigned)n_fp, (unsigned)chunks);
-    kernel<<<grid, PF_THREADS, smem, stream>>>(p);
+    kernel<<<grid, PF_THREADS, smem, stream>>>(q);
     PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
