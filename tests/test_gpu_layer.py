@@ -54,6 +54,9 @@ def test_flat_layer_on_a_tensor_mesh_takes_the_marching_kernel(name):
     assert rowwise_rel(sim.G.to_numpy(), case["G"]).max() <= RTOL_NORMWISE
     fo = layer_simulation(case, store="forward_only", mesh=mesh)
     assert vec_rel(fo.dpred(case["model"]), case["fwd"]) <= RTOL_NORMWISE
+    assert vec_rel(fo.Jtvec(case["model"], case["v"]), case["gtv"]) <= RTOL_NORMWISE
+    expected = np.einsum("i,ij,ij->j", case["w"], case["G"], case["G"])
+    assert vec_rel(fo._gtg_diagonal_without_building_g(case["w"]), expected) <= RTOL_NORMWISE
 
 
 def test_layer_float32_storage():
