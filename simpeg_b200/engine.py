@@ -21,6 +21,13 @@ _G_ALIGN = 16  # leading dimension of G in elements (128 B rows for fp64)
 _PINNED = {"turn": 0, "bufs": [None, None], "events": [None, None]}
 
 
+def _pieces(n, min_piece=1 << 19, max_pieces=4):
+    """Split [0, n) into at most ``max_pieces`` ranges of at least ``min_piece`` doubles (4 MB)."""
+    k = max(1, min(max_pieces, n // min_piece))
+    bounds = [n * j // k for j in range(k + 1)]
+    return [(bounds[j], bounds[j + 1]) for j in range(k) if bounds[j + 1] > bounds[j]] or [(0, 0)]
+
+
 def _require_cuda():
     import torch
 
@@ -185,11 +192,15 @@ class CudaEngine:
         if n is not None and a.shape[0] != n:
             raise ValueError(f"expected a vector of length {n}, got {a.shape[0]}")
         torch = self.torch
-        i, pin = self._pinned(a.shape[0])
-        self.lib.pf_host_copy(pin.data_ptr(), a.ctypes.data, a.nbytes)
+        n = a.shape[0]
+        i, pin = self._pinned(n)
         with torch.cuda.device(self.device):
-            dev = torch.empty(a.shape[0], dtype=torch.float64, device=self.device)
-            dev.copy_(pin, non_blocking=True)
+            dev = torch.empty(n, dtype=torch.float64, device=self.device)
+            # long vectors in a few pieces: the async H2D of one piece overlaps the staging copy
+            # of the next
+            for lo, hi in _pieces(n):
+                self.lib.pf_host_copy(pin.data_ptr() + 8 * lo, a.ctypes.data + 8 * lo, 8 * (hi - lo))
+                dev[lo:hi].copy_(pin[lo:hi], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
         _PINNED["events"][i] = ev
@@ -201,14 +212,20 @@ class CudaEngine:
         t = tensor.detach().reshape(-1)
         if t.dtype != torch.float64 or t.device.type != "cuda":
             return t.cpu().numpy()
-        i, pin = self._pinned(t.numel())
+        n = t.numel()
+        i, pin = self._pinned(n)
+        pieces = _pieces(n)
+        events = []
         with torch.cuda.device(self.device):
-            pin.copy_(t, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-        ev.synchronize()
-        out = np.empty(t.numel(), dtype=np.float64)
-        self.lib.pf_host_copy(out.ctypes.data, pin.data_ptr(), out.nbytes)
+            for lo, hi in pieces:
+                pin[lo:hi].copy_(t[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+        out = np.empty(n, dtype=np.float64)
+        for (lo, hi), ev in zip(pieces, events):      # staging copy of a piece while the next one arrives
+            ev.synchronize()
+            self.lib.pf_host_copy(out.ctypes.data + 8 * lo, pin.data_ptr() + 8 * lo, 8 * (hi - lo))
         return out
 
     def _jp(self, job):
