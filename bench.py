@@ -258,6 +258,7 @@ def run_cuda(args):
     import torch.distributed as dist
 
     from simpeg_b200.engine import launch_count, probe_fp64_peak
+    from simpeg_b200.potential_fields.base import SLICED_UPLOAD_MIN
     from simpeg_b200.sharding import Collectives
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -432,7 +433,9 @@ def run_cuda(args):
         plan_arrays = [plan.tile_xyz, plan.tile_cell_nodes, plan.tile_cell_col, plan.tile_n_nodes,
                        plan.grid_colmap, plan.footprints4, plan.footprints2] + list(plan.grid_axes or [])
         h2d = (sum(a.nbytes for a in plan_arrays if a is not None)
-               + sim2._sharding.local_rows.size // len(wl["components"]) * 24 + 8 * (nP + nD))
+               + sim2._sharding.local_rows.size // len(wl["components"]) * 24
+               # Jvec argument: every rank uploads its 1/world slice (all-gathered over NVLink)
+               + 8 * (-(-nP // world) if (world > 1 and nP >= SLICED_UPLOAD_MIN) else nP) + 8 * nD)
         d2h = 8 * (nD + nP)
         checksum = float(np.sum(jv)) + float(np.sum(jtv))
         del sim2, plan

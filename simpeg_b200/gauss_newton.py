@@ -188,7 +188,7 @@ class DeviceGaussNewtonCG:
     def hessian_vector(self, v):
         """``H v = 2 J^T W^T W J v + beta R v`` for a host vector (device round trip; tests)."""
         eng = self.engine
-        p = eng.to_device(v, n=self.nP)
+        p = self.ops.cols_to_device(v)
         q = self.torch.empty_like(p)
         with self.torch.cuda.device(eng.device):
             self._hvp_combine(self._normal_product(p), p, q, None)
@@ -226,10 +226,10 @@ class DeviceGaussNewtonCG:
         ws, wsb = self._ws.data_ptr(), self._ws.numel() * 8
         with torch.cuda.device(eng.device):
             stream = eng._stream()
-            g_t = eng.to_device(g)
+            g_t = self.ops.cols_to_device(g)
             mask = None if inactive.all() else torch.from_numpy(inactive.astype(np.uint8)).to(eng.device)
             if self._approx_hinv is not None and self._minv_t is None:
-                self._minv_t = eng.to_device(self._approx_hinv, n=n)
+                self._minv_t = self.ops.cols_to_device(self._approx_hinv)
             minv = self._minv_t
             step, r, p, q, h = (torch.empty(n, dtype=torch.float64, device=eng.device) for _ in range(5))
             scal = self._scal

@@ -127,6 +127,23 @@ class Collectives:
             self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
         return tensor
 
+    def all_gather_slices(self, make_slice, n):
+        """Full (n,) device vector from equal slices: rank r provides ``make_slice(lo, hi)`` for its
+        block of ``ceil(n / world)`` entries (the last block may be short and is padded)."""
+        import torch
+
+        m = -(-int(n) // self.world_size)
+        lo = min(self.rank * m, n)
+        hi = min(lo + m, n)
+        piece = make_slice(lo, hi)
+        if hi - lo < m:
+            padded = torch.zeros(m, dtype=piece.dtype, device=piece.device)
+            padded[: hi - lo] = piece
+            piece = padded
+        full = torch.empty(m * self.world_size, dtype=piece.dtype, device=piece.device)
+        self._dist.all_gather_into_tensor(full, piece.contiguous(), group=self.group)
+        return full[:n]
+
     def all_gather_rows(self, local, sharding: ReceiverSharding):
         """Assemble the full (nD,) vector from every rank's local rows (dpred, Jvec)."""
         import torch

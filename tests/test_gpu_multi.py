@@ -30,7 +30,9 @@ def _worker(rank, world, port, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         from sim_fixtures import magnetic_survey, make_mapping, small_mesh, susceptibilities
-        from simpeg_b200.potential_fields import magnetics
+        from simpeg_b200.potential_fields import base, magnetics
+
+        base.SLICED_UPLOAD_MIN = 0      # exercise the rank-sliced upload + all-gather of model vectors
 
         mesh = small_mesh()
         out = {}

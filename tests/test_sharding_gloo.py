@@ -41,6 +41,12 @@ def _worker(rank, world, port, name, out_dir):
         assert np.array_equal(G_local, case["G"][sh.local_rows])           # row ownership
         fwd = coll.all_gather_rows(torch.from_numpy(local.forward(case["model"])), sh).numpy()
         gtv = coll.all_reduce_sum(torch.from_numpy(local.gt_dot_v(case["v"][sh.local_rows]))).numpy()
+        # replicated host vector uploaded in rank slices and all-gathered (odd length: padded tail)
+        model = case["model"]
+        full = coll.all_gather_slices(lambda lo, hi: torch.from_numpy(model[lo:hi].copy()), model.size)
+        assert np.array_equal(full.numpy(), model)
+        odd = np.arange(7.0)
+        assert np.array_equal(coll.all_gather_slices(lambda lo, hi: torch.from_numpy(odd[lo:hi].copy()), 7).numpy(), odd)
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), fwd=fwd, gtv=gtv)
     finally:
         dist.destroy_process_group()
