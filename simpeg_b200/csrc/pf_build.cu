@@ -535,12 +535,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
             const char *pl = reinterpret_cast<const char *>(planes);
             const bool emit = L > iz_begin;
             int col[NR];
+            const int layer_off = (int)(layer_stride * (L - 1));   // mesh cells < 2^31 (validate_grid)
+            const int32_t *colmap = p.plan.grid_colmap;
 #pragma unroll
             for (int s = 0; s < NR; ++s) {
                 col[s] = -1;
                 if (emit && cbase[s] >= 0) {
-                    const int64_t idx = cbase[s] + layer_stride * (L - 1);
-                    col[s] = p.plan.grid_colmap ? __ldg(p.plan.grid_colmap + idx) : (int)idx;
+                    const int idx = cbase[s] + layer_off;
+                    col[s] = colmap ? __ldg(colmap + idx) : idx;
                 }
             }
             double fsum = 0.0;
@@ -1202,6 +1204,8 @@ int validate_grid(const pf_plan *plan)
 {
     if (plan->grid_nx == 0) return PF_OK;
     PF_CHECK_ARG(plan->grid_nx > 0 && plan->grid_ny > 0 && plan->grid_nz > 0, "bad grid shape");
+    PF_CHECK_ARG((int64_t)plan->grid_nx * plan->grid_ny * plan->grid_nz < ((int64_t)1 << 31),
+                 "tensor mesh with 2^31 or more cells");
     PF_CHECK_ARG(plan->grid_xs && plan->grid_ys && plan->grid_zs, "null grid axis");
     PF_CHECK_ARG(plan->n_footprints4 >= 0 && plan->n_footprints2 >= 0, "negative footprint count");
     PF_CHECK_ARG(plan->n_footprints4 == 0 || plan->footprints4, "null footprints4");
