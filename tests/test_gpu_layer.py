@@ -216,3 +216,31 @@ def test_fit_gravity_equivalent_sources(top_bottom_as_array):
         m = m + solver.find_search_direction(g)             # linear problem: full Newton step
         solver.beta /= 3.0                                  # BetaSchedule(coolingFactor=3, coolingRate=1)
     np.testing.assert_allclose(sim.dpred(m), dobs, atol=0.005, rtol=1e-5)
+
+
+def test_layer_edge_cases_single_cell_and_no_receivers():
+    """One prism / an empty receiver object / no active cells (shapes only: nothing to evaluate)."""
+    from oracle.oracle import OracleLayerSimulation
+    from simpeg_b200 import maps
+    from simpeg_b200.meshes import CellBoundsMesh2D
+    from simpeg_b200.potential_fields import gravity
+
+    mesh = CellBoundsMesh2D(np.array([[-5.0, 5.0, -2.0, 4.0]]))
+    loc = np.array([[0.0, 1.0, 2.0], [20.0, -3.0, 1.0], [-5.0, -2.0, 0.5]])   # last one above a corner
+    rx = gravity.receivers.Point(loc, components=["gz", "gxy"])
+    empty = gravity.receivers.Point(np.zeros((0, 3)), components=["gx"])
+    survey = gravity.survey.Survey(gravity.sources.SourceField([empty, rx]))
+    sim = gravity.SimulationEquivalentSourceLayer(mesh, -1.0, -3.0, survey=survey,
+                                                  rhoMap=maps.IdentityMap(nP=1), sensitivity_dtype=np.float64)
+    ref = OracleLayerSimulation("gravity", mesh.cell_bounds, -1.0, -3.0,
+                                [(np.zeros((0, 3)), ["gx"]), (loc, ["gz", "gxy"])])
+    G = sim.G.to_numpy()
+    assert G.shape == (6, 1)
+    assert rowwise_rel(G, ref.sensitivity_matrix()).max() <= RTOL_NORMWISE
+    assert vec_rel(sim.dpred(np.array([0.3])), ref.forward(np.array([0.3]))) <= RTOL_NORMWISE
+    # no active cells at all
+    none = gravity.SimulationEquivalentSourceLayer(mesh, np.zeros(0), np.zeros(0), survey=survey,
+                                                   active_cells=np.array([False]),
+                                                   rhoMap=maps.IdentityMap(nP=0), sensitivity_dtype=np.float64)
+    assert none.G.shape == (6, 0)
+    assert np.array_equal(none.dpred(np.zeros(0)), np.zeros(6))
