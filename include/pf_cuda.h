@@ -289,6 +289,21 @@ int pf_cg_update(const double *p, const double *q, const double *minv, int64_t n
 int pf_cg_direction(const double *h, int64_t n, double *p, double *scal, void *stream);
 int pf_vec_mul(const double *a, const double *b, int64_t n, double *out, void *stream);
 
+/*
+ * Host-side generic tile planner (HOST pointers; no CUDA calls): recursive coordinate bisection of
+ * the (nodes, cell_nodes) tables BasePFSimulation._get_active_nodes returns (base.py:371-399) --
+ * tree meshes with hanging nodes, equivalent-source layers.  pf_plan_generic_assign writes the
+ * tile of every cell (<= 512 cells and <= 768 distinct nodes per tile) and returns the number of
+ * tiles; pf_plan_generic_fill then fills tile_xyz[n_tiles][3][768], tile_cell_nodes[n_tiles][512][8],
+ * tile_cell_col[n_tiles][512] (-1 = padding) and tile_n_nodes[n_tiles].
+ */
+int64_t pf_plan_generic_assign(const double *nodes, int64_t n_nodes, const int64_t *cell_nodes,
+                               int64_t n_cells, int32_t *tile_of_cell);
+int pf_plan_generic_fill(const double *nodes, int64_t n_nodes, const int64_t *cell_nodes,
+                         int64_t n_cells, const int32_t *tile_of_cell, int64_t n_tiles,
+                         double *tile_xyz, uint16_t *tile_cell_nodes, int32_t *tile_cell_col,
+                         int32_t *tile_n_nodes);
+
 /* Host staging copy (HOST pointers, a few threads): numpy vector <-> pinned staging buffer of the
  * H2D / D2H transfers around the products (the boundary cost of SURVEY.md 8(b) "Callers across
  * the boundary"). */

@@ -10,6 +10,8 @@
 // the tile arrays are produced straight from the 1-D node coordinates and the
 // list of active cells, without materialising (nodes, cell_nodes).
 #include <algorithm>
+#include <cmath>
+#include <utility>
 #include <vector>
 
 #include "pf_common.cuh"
@@ -140,6 +142,247 @@ extern "C" int pf_plan_tensor_fill(int64_t nx, int64_t ny, int64_t nz, const dou
             cn[v] = (uint16_t)((lx + dx) + w1 * ((ly + dy) + h1 * (lz + dz)));
         }
     }
+    return PF_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Generic tile planner: recursive coordinate bisection of arbitrary (nodes, cell_nodes) tables --
+// tree meshes with hanging nodes, equivalent-source layers, anything _get_active_nodes
+// (base.py:371-399) can return.  Same rule as the numpy version it replaces
+// (simpeg_b200/tiling.py::_rcb_tile_ids): a region is a tile when it has <= 512 cells whose
+// vertices are <= 768 distinct nodes; otherwise it is cut, across its longest axis, BETWEEN two
+// distinct cell-centre coordinates as close to the median as possible (cells in one plane stay
+// together).  Every level is a handful of O(n) passes (selection, not sorting).
+// ---------------------------------------------------------------------------
+namespace {
+
+struct RcbPlanner {
+    const int64_t *cn;
+    int64_t n_nodes;
+    std::vector<double> c[3];         // cell centres
+    std::vector<int32_t> ids;         // permutation of the cells, regions are sub-ranges
+    std::vector<int32_t> stamp;       // last region id that touched a node
+    std::vector<double> vals;         // scratch: coordinates of a region
+    int32_t stamp_id = 0;
+    int32_t *tile_of_cell;
+    int32_t n_tiles = 0;
+
+    bool fits(int64_t lo, int64_t hi)
+    {
+        if (hi - lo > PF_TILE_CELLS) return false;
+        ++stamp_id;
+        int count = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t *v = cn + 8 * (int64_t)ids[i];
+            for (int k = 0; k < 8; ++k) {
+                if (stamp[v[k]] != stamp_id) {
+                    stamp[v[k]] = stamp_id;
+                    if (++count > PF_TILE_NODES) return false;
+                }
+            }
+        }
+        return true;
+    }
+
+    // position m in (lo, hi) such that [lo, m) / [m, hi) are the two sides of the cut, or -1 when
+    // every centre of the region has the same coordinate along `ax`
+    int64_t cut(int64_t lo, int64_t hi, int ax)
+    {
+        const int64_t n = hi - lo;
+        const std::vector<double> &x = c[ax];
+        vals.resize((size_t)n);
+        double vmin = x[ids[lo]], vmax = vmin;
+        for (int64_t i = 0; i < n; ++i) {
+            const double v = x[ids[lo + i]];
+            vals[i] = v;
+            vmin = std::min(vmin, v);
+            vmax = std::max(vmax, v);
+        }
+        if (!(vmax > vmin)) return -1;
+        // np.median: mean of the two middle elements for even n
+        std::nth_element(vals.begin(), vals.begin() + n / 2, vals.end());
+        double med = vals[n / 2];
+        if (n % 2 == 0) med = 0.5 * (med + *std::max_element(vals.begin(), vals.begin() + n / 2));
+        // distinct neighbours of the median: a = largest value <= med, a_prev = largest < a,
+        // b = smallest > med
+        double a = vmin, b = vmax;
+        bool has_b = false;
+        for (int64_t i = 0; i < n; ++i) {
+            const double v = vals[i];
+            if (v <= med) { if (v > a) a = v; }
+            else if (!has_b || v < b) { b = v; has_b = true; }
+        }
+        double a_prev = 0.0;
+        bool has_prev = false;
+        for (int64_t i = 0; i < n; ++i) {
+            const double v = vals[i];
+            if (v < a && (!has_prev || v > a_prev)) { a_prev = v; has_prev = true; }
+        }
+        double best = 0.0;
+        bool have = false;
+        if (has_prev) { best = 0.5 * (a_prev + a); have = true; }      // lower cut first (argmin ties)
+        if (has_b) {
+            const double c2 = 0.5 * (a + b);
+            if (!have || std::fabs(c2 - med) < std::fabs(best - med)) best = c2;
+            have = true;
+        }
+        if (!have) return -1;
+        const double cutv = best;
+        int32_t *first = ids.data() + lo, *last = ids.data() + hi;
+        int32_t *mid = std::stable_partition(first, last, [&](int32_t id) { return x[id] < cutv; });
+        const int64_t m = lo + (mid - first);
+        return (m > lo && m < hi) ? m : -1;
+    }
+
+    void run(int64_t n_cells)
+    {
+        std::vector<std::pair<int64_t, int64_t>> stack;
+        stack.emplace_back(0, n_cells);
+        while (!stack.empty()) {
+            const auto [lo, hi] = stack.back();
+            stack.pop_back();
+            if (hi <= lo) continue;
+            if (fits(lo, hi)) {
+                for (int64_t i = lo; i < hi; ++i) tile_of_cell[ids[i]] = n_tiles;
+                ++n_tiles;
+                continue;
+            }
+            // axes by decreasing extent
+            double ext[3];
+            for (int ax = 0; ax < 3; ++ax) {
+                double mn = c[ax][ids[lo]], mx = mn;
+                for (int64_t i = lo; i < hi; ++i) {
+                    const double v = c[ax][ids[i]];
+                    mn = std::min(mn, v);
+                    mx = std::max(mx, v);
+                }
+                ext[ax] = mx - mn;
+            }
+            int order[3] = {0, 1, 2};
+            std::stable_sort(order, order + 3, [&](int p, int q) { return ext[p] > ext[q]; });
+            int64_t m = -1;
+            for (int t = 0; t < 3 && m < 0; ++t) m = cut(lo, hi, order[t]);
+            if (m < 0) m = lo + (hi - lo) / 2;       // all centres coincide: split by count
+            stack.emplace_back(m, hi);
+            stack.emplace_back(lo, m);
+        }
+    }
+};
+
+}  // namespace
+
+// tile_of_cell[c] = tile of cell c; returns the number of tiles (or a negative pf_status)
+extern "C" int64_t pf_plan_generic_assign(const double *nodes /*[nN][3]*/, int64_t n_nodes,
+                                          const int64_t *cell_nodes /*[nC][8]*/, int64_t n_cells,
+                                          int32_t *tile_of_cell)
+{
+    if (n_cells < 0 || n_nodes < 0 || (n_cells > 0 && (!nodes || !cell_nodes || !tile_of_cell))) {
+        pf_set_error("pf_plan_generic_assign: bad arguments");
+        return PF_ERR_INVALID;
+    }
+    if (n_cells >= ((int64_t)1 << 31) || n_nodes >= ((int64_t)1 << 31)) {
+        pf_set_error("pf_plan_generic_assign: more than 2^31-1 cells or nodes");
+        return PF_ERR_INVALID;
+    }
+    RcbPlanner r;
+    r.cn = cell_nodes;
+    r.n_nodes = n_nodes;
+    r.tile_of_cell = tile_of_cell;
+    for (int ax = 0; ax < 3; ++ax) r.c[ax].resize((size_t)n_cells);
+    r.ids.resize((size_t)n_cells);
+    r.stamp.assign((size_t)n_nodes, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(4) reduction(| : bad)
+    for (int64_t cidx = 0; cidx < n_cells; ++cidx) {
+        const int64_t *v = cell_nodes + 8 * cidx;
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < 8; ++k) {
+            if (v[k] < 0 || v[k] >= n_nodes) { bad = 1; continue; }
+            for (int ax = 0; ax < 3; ++ax) s[ax] += nodes[3 * v[k] + ax];
+        }
+        for (int ax = 0; ax < 3; ++ax) r.c[ax][cidx] = 0.125 * s[ax];
+        r.ids[cidx] = (int32_t)cidx;
+    }
+    if (bad) {
+        pf_set_error("pf_plan_generic_assign: cell_nodes holds indices outside the nodes array");
+        return PF_ERR_INVALID;
+    }
+    r.run(n_cells);
+    return r.n_tiles;
+}
+
+// Fills the pf_plan arrays for a given assignment: cells of a tile in ascending index order
+// (contiguous G writes), local node ids in ascending node order.
+extern "C" int pf_plan_generic_fill(const double *nodes, int64_t n_nodes, const int64_t *cell_nodes,
+                                    int64_t n_cells, const int32_t *tile_of_cell, int64_t n_tiles,
+                                    double *tile_xyz, uint16_t *tile_cell_nodes, int32_t *tile_cell_col,
+                                    int32_t *tile_n_nodes)
+{
+    PF_CHECK_ARG(n_cells >= 0 && n_tiles >= 0, "negative size");
+    if (n_cells == 0 || n_tiles == 0) return PF_OK;
+    PF_CHECK_ARG(nodes && cell_nodes && tile_of_cell && tile_xyz && tile_cell_nodes && tile_cell_col && tile_n_nodes,
+                 "null pointer");
+    std::vector<int64_t> start((size_t)n_tiles + 1, 0);
+    for (int64_t cidx = 0; cidx < n_cells; ++cidx) {
+        const int32_t t = tile_of_cell[cidx];
+        PF_CHECK_ARG(t >= 0 && t < n_tiles, "tile id out of range");
+        ++start[(size_t)t + 1];
+    }
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        PF_CHECK_ARG(start[(size_t)t + 1] <= PF_TILE_CELLS, "tile with too many cells");
+        start[(size_t)t + 1] += start[(size_t)t];
+    }
+    std::vector<int32_t> cells((size_t)n_cells);
+    {
+        std::vector<int64_t> pos(start.begin(), start.end() - 1);
+        for (int64_t cidx = 0; cidx < n_cells; ++cidx) cells[(size_t)pos[(size_t)tile_of_cell[cidx]]++] = (int32_t)cidx;
+    }
+    int failed = 0;
+#pragma omp parallel num_threads(4)
+    {
+        std::vector<int32_t> local((size_t)n_nodes, -1);      // per thread: global node -> local id
+        std::vector<int64_t> uniq;
+        uniq.reserve(PF_TILE_NODES + 8);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            uniq.clear();
+            for (int64_t i = start[(size_t)t]; i < start[(size_t)t + 1]; ++i) {
+                const int64_t *v = cell_nodes + 8 * (int64_t)cells[(size_t)i];
+                for (int k = 0; k < 8; ++k)
+                    if (local[(size_t)v[k]] < 0) { local[(size_t)v[k]] = 0; uniq.push_back(v[k]); }
+            }
+            if ((int64_t)uniq.size() > PF_TILE_NODES) {
+                failed = 1;
+                for (int64_t g : uniq) local[(size_t)g] = -1;
+                continue;
+            }
+            std::sort(uniq.begin(), uniq.end());
+            double *xyz = tile_xyz + t * 3 * (int64_t)PF_TILE_NODES;
+            for (size_t j = 0; j < uniq.size(); ++j) {
+                local[(size_t)uniq[j]] = (int32_t)j;
+                for (int ax = 0; ax < 3; ++ax) xyz[ax * PF_TILE_NODES + (int64_t)j] = nodes[3 * uniq[j] + ax];
+            }
+            for (size_t j = uniq.size(); j < (size_t)PF_TILE_NODES; ++j)
+                for (int ax = 0; ax < 3; ++ax) xyz[ax * PF_TILE_NODES + (int64_t)j] = 0.0;
+            tile_n_nodes[t] = (int32_t)uniq.size();
+            int64_t slot = 0;
+            for (int64_t i = start[(size_t)t]; i < start[(size_t)t + 1]; ++i, ++slot) {
+                const int64_t cidx = cells[(size_t)i];
+                const int64_t *v = cell_nodes + 8 * cidx;
+                uint16_t *out = tile_cell_nodes + (t * PF_TILE_CELLS + slot) * 8;
+                for (int k = 0; k < 8; ++k) out[k] = (uint16_t)local[(size_t)v[k]];
+                tile_cell_col[t * PF_TILE_CELLS + slot] = (int32_t)cidx;
+            }
+            for (; slot < PF_TILE_CELLS; ++slot) {
+                uint16_t *out = tile_cell_nodes + (t * PF_TILE_CELLS + slot) * 8;
+                for (int k = 0; k < 8; ++k) out[k] = 0;
+                tile_cell_col[t * PF_TILE_CELLS + slot] = -1;
+            }
+            for (int64_t g : uniq) local[(size_t)g] = -1;
+        }
+    }
+    PF_CHECK_ARG(!failed, "tile with too many nodes");
     return PF_OK;
 }
 

@@ -346,7 +346,9 @@ class BasePFSimulation:
         if axes is not None:
             active = None if self.nC == self.mesh.n_cells else np.nonzero(self.active_cells)[0]
             return build_tile_plan_tensor(axes, active, with_tiles=False)
-        return self._cached_generic_plan(lambda: build_tile_plan(*self._get_active_nodes()))
+        # tree meshes go straight to the bisection (the brick test costs more than the plan)
+        method = "rcb" if hasattr(self.mesh, "total_nodes") else "auto"
+        return self._cached_generic_plan(lambda: build_tile_plan(*self._get_active_nodes(), method))
 
     def _cached_generic_plan(self, build):
         """The generic (nodes, cell_nodes) planner costs seconds per million cells and depends only
@@ -621,4 +623,5 @@ class BaseEquivalentSourceLayerSimulation(BasePFSimulation):
 
         self._plan_cache_tag = "layer:" + hashlib.sha1(
             np.ascontiguousarray(top).tobytes() + np.ascontiguousarray(bot).tobytes()).hexdigest()
-        return self._cached_generic_plan(lambda: build_tile_plan(*self._get_active_nodes()))
+        method = "auto" if flat else "rcb"      # only a flat layer can be brick-like
+        return self._cached_generic_plan(lambda: build_tile_plan(*self._get_active_nodes(), method))

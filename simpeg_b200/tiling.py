@@ -384,46 +384,46 @@ def build_tile_plan(nodes, cell_nodes, method="auto") -> TilePlan:
         return TilePlan(0, 0, np.zeros((0, 3, TILE_NODES)), np.zeros((0, TILE_CELLS, 8), np.uint16),
                         np.zeros((0, TILE_CELLS), np.int32), np.zeros(0, np.int32), "empty")
 
-    centers = _cell_centers(nodes, cell_nodes)
+    from . import _lib
+
+    lib = _lib.load_library()
+    ptr = lambda a: a.ctypes.data  # noqa: E731
     tile = None
     used = method
     if method in ("auto", "brick"):
+        centers = _cell_centers(nodes, cell_nodes)
         tile = _brick_tile_ids(centers)
         used = "brick"
         if tile is None and method == "brick":
             raise ValueError("mesh is not tensor-like; use method='rcb'")
-    if tile is None:
+        if tile is not None:
+            _, tile = np.unique(tile, return_inverse=True)  # compact (bricks may be empty)
+            tile = _enforce_limits(tile.astype(np.int64), centers, cell_nodes)
+    if tile is None and method == "rcb_numpy":
+        # the numpy version of the bisection (kept as the readable statement of the rule and as a
+        # cross-check of the native planner in the tests)
+        centers = _cell_centers(nodes, cell_nodes)
         tile = _rcb_tile_ids(centers, cell_nodes)
+        _, tile = np.unique(tile, return_inverse=True)
+        tile = _enforce_limits(tile.astype(np.int64), centers, cell_nodes)
         used = "rcb"
-    _, tile = np.unique(tile, return_inverse=True)  # compact (bricks may be empty)
-    tile = _enforce_limits(tile.astype(np.int64), centers, cell_nodes)
-    n_tiles = int(tile.max()) + 1
+    if tile is None:
+        # native recursive coordinate bisection (csrc/pf_plan.cu), O(n) per level
+        tile32 = np.empty(n_cells, dtype=np.int32)
+        n_tiles = int(lib.pf_plan_generic_assign(ptr(nodes), n_nodes, ptr(cell_nodes), n_cells, ptr(tile32)))
+        _lib.check(min(n_tiles, 0), "pf_plan_generic_assign")
+        used = "rcb"
+    else:
+        tile32 = np.ascontiguousarray(tile, dtype=np.int32)
+        n_tiles = int(tile32.max()) + 1
 
-    # ---- cells: slots ordered by original index inside each tile -------------
-    order = np.argsort(tile, kind="stable")  # stable: ascending column inside a tile
-    counts = np.bincount(tile, minlength=n_tiles)
-    starts = np.r_[0, np.cumsum(counts)[:-1]]
-    pos = np.arange(n_cells) - np.repeat(starts, counts)
-    slot = tile[order] * TILE_CELLS + pos
-    tile_cell_col = np.full(n_tiles * TILE_CELLS, -1, dtype=np.int32)
-    tile_cell_col[slot] = order.astype(np.int32)
-
-    # ---- nodes: unique (tile, node) pairs, local ids in ascending node order ---
-    key = (tile[:, None] * np.int64(n_nodes) + cell_nodes).ravel()
-    ukey, inv = np.unique(key, return_inverse=True)
-    utile = ukey // n_nodes
-    unode = ukey - utile * n_nodes
-    ncounts = np.bincount(utile, minlength=n_tiles)
-    if ncounts.max() > TILE_NODES or counts.max() > TILE_CELLS:
-        raise RuntimeError("tile planner produced an oversized tile")  # pragma: no cover
-    nstarts = np.r_[0, np.cumsum(ncounts)[:-1]]
-    local = (inv - nstarts[utile[inv]]).reshape(n_cells, 8)
-    tile_cell_nodes = np.zeros((n_tiles * TILE_CELLS, 8), dtype=np.uint16)
-    tile_cell_nodes[slot] = local[order].astype(np.uint16)
-    npos = np.arange(len(ukey)) - np.repeat(nstarts, ncounts)
-    tile_xyz = np.zeros((n_tiles, 3, TILE_NODES), dtype=np.float64)
-    for ax in range(3):
-        tile_xyz[utile, ax, npos] = nodes[unode, ax]
+    tile_xyz = np.empty((n_tiles, 3, TILE_NODES), dtype=np.float64)
+    tile_cell_nodes = np.empty((n_tiles * TILE_CELLS, 8), dtype=np.uint16)
+    tile_cell_col = np.empty(n_tiles * TILE_CELLS, dtype=np.int32)
+    ncounts = np.empty(n_tiles, dtype=np.int32)
+    _lib.check(lib.pf_plan_generic_fill(ptr(nodes), n_nodes, ptr(cell_nodes), n_cells, ptr(tile32), n_tiles,
+                                        ptr(tile_xyz), ptr(tile_cell_nodes), ptr(tile_cell_col),
+                                        ptr(ncounts)), "pf_plan_generic_fill")
 
     return TilePlan(n_tiles, n_cells, tile_xyz,
                     tile_cell_nodes.reshape(n_tiles, TILE_CELLS, 8),

@@ -63,7 +63,12 @@ def test_octree_with_hanging_nodes():
     widths = np.unique(np.round(mesh.cell_volumes ** (1 / 3), 6))
     assert len(widths) == 3              # three refinement levels present
     check_plan(mesh.total_nodes, mesh.cell_nodes)
-    check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb")
+    native = check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb")
+    # the native planner (csrc/pf_plan.cu) follows the same bisection rule as the numpy statement
+    # of it: same tiles (up to numbering), hence the same number of node evaluations
+    numpy_plan = check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb_numpy")
+    assert native.n_tiles == numpy_plan.n_tiles
+    assert native.node_evaluations == numpy_plan.node_evaluations
 
 
 def _check_tensor_plan(mesh, active=None):
