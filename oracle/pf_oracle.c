@@ -12,7 +12,7 @@
  * --impl reference legs may load this library.  The product (simpeg_b200/)
  * never does: it fails loudly when its CUDA library is missing.
  *
- * Parity pinning: this file is checked (tests/test_oracle_vs_reference.py,
+ * Parity pinning: this file is checked (tests/test_oracle_golden.py,
  * and the committed tests/golden npz files made by oracle/make_golden.py) against
  * the reference's own UNMODIFIED numba files
  *     simpeg/potential_fields/_numba_utils.py

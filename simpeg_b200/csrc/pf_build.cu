@@ -1087,7 +1087,7 @@ constexpr int MAX_PASSES = 2 * PF_MAX_COMPONENTS;
 // receivers per chunk: enough CTAs to fill the machine a few times over
 int choose_rc(int64_t n_tiles, int64_t n_receivers, int64_t max_chunks)
 {
-    const int64_t target_ctas = 148 * 2 * 8;
+    const int64_t target_ctas = (int64_t)pf_sm_count() * 2 * 8;
     int64_t chunks = pf_ceil_div(target_ctas, n_tiles > 0 ? n_tiles : 1);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
@@ -1273,14 +1273,39 @@ extern "C" int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64
     return PF_OK;
 }
 
-extern "C" int64_t pf_forward_workspace_bytes(const pf_plan *plan, const pf_job *job)
+namespace {
+// forward partial sums: [parts][receivers of the chunk][components] doubles.  For tree meshes and
+// layers `parts` is the number of tiles (~ nC / 512), so the receivers of a job are processed in
+// chunks whose partials stay below FWD_WS_CAP (>= FWD_MIN_RX receivers per chunk)
+constexpr int64_t FWD_WS_CAP = (int64_t)256 << 20;
+constexpr int64_t FWD_MIN_RX = 64;
+
+int64_t forward_parts(const pf_plan *plan)
 {
-    if (!plan || !job) return -1;
     int64_t parts = plan->n_tiles;
     if (plan->n_footprints4 > parts) parts = plan->n_footprints4;
     if (plan->n_footprints2 > parts) parts = plan->n_footprints2;
-    return parts * job->n_receivers * (int64_t)job->n_components * (int64_t)sizeof(double);
+    return parts > 0 ? parts : 1;
 }
+
+int64_t forward_bytes_per_receiver(const pf_plan *plan, const pf_job *job)
+{
+    return forward_parts(plan) * (int64_t)job->n_components * (int64_t)sizeof(double);
+}
+}  // namespace
+
+extern "C" int64_t pf_forward_workspace_bytes(const pf_plan *plan, const pf_job *job)
+{
+    if (!plan || !job) return -1;
+    const int64_t per_rx = forward_bytes_per_receiver(plan, job);
+    int64_t rx = FWD_WS_CAP / per_rx;
+    if (rx < FWD_MIN_RX) rx = FWD_MIN_RX;
+    if (rx > job->n_receivers) rx = job->n_receivers;
+    return rx * per_rx;
+}
+
+static int pf_forward_chunk(const pf_plan *plan, const pf_job *job, const double *model, double *fields,
+                            void *workspace, void *stream);
 
 extern "C" int pf_forward(const pf_plan *plan, const pf_job *job, const double *model,
                           double *fields, void *workspace, int64_t workspace_bytes, void *stream)
@@ -1291,10 +1316,27 @@ extern "C" int pf_forward(const pf_plan *plan, const pf_job *job, const double *
     PF_CHECK_ARG(model && fields, "null model or fields");
     st = validate_grid(plan);
     if (st != PF_OK) return st;
-    if (workspace_bytes < pf_forward_workspace_bytes(plan, job) || !workspace) {
+    const int64_t per_rx = forward_bytes_per_receiver(plan, job);
+    const int64_t rx_chunk = workspace ? workspace_bytes / per_rx : 0;
+    if (rx_chunk < 1 || workspace_bytes < pf_forward_workspace_bytes(plan, job)) {
         pf_set_error("pf_forward: workspace too small");
         return PF_ERR_WORKSPACE;
     }
+    for (int64_t r0 = 0; r0 < job->n_receivers; r0 += rx_chunk) {
+        pf_job sub = *job;
+        sub.receivers = job->receivers + 3 * r0;
+        sub.n_receivers = (job->n_receivers - r0 < rx_chunk) ? job->n_receivers - r0 : rx_chunk;
+        sub.row_offset = job->row_offset + r0 * job->n_components;
+        st = pf_forward_chunk(plan, &sub, model, fields, workspace, stream);
+        if (st != PF_OK) return st;
+    }
+    return PF_OK;
+}
+
+static int pf_forward_chunk(const pf_plan *plan, const pf_job *job, const double *model, double *fields,
+                            void *workspace, void *stream)
+{
+    int st = PF_OK;
     static thread_local Pass passes[MAX_PASSES];
     const int n = make_passes(plan, job, passes, MAX_PASSES);
     PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");

@@ -22,6 +22,7 @@ constexpr int PF_NPT = PF_TILE_NODES / PF_THREADS;
 constexpr double PF_NEWTON_G = 6.6743e-11;
 
 void pf_set_error(const char *fmt, ...);
+int pf_sm_count(void);   // SMs of the current device (pf_abi.cu)
 extern std::atomic<int64_t> g_pf_launches;
 #define PF_COUNT_LAUNCH() (g_pf_launches.fetch_add(1, std::memory_order_relaxed))
 

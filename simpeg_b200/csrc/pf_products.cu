@@ -72,7 +72,8 @@ template <> struct XType<float> { using type = float; };
 template <typename GT, bool ALIGNED>
 __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G, int64_t rows, int64_t cols,
                                                         int64_t ld, const double *__restrict__ x,
-                                                        double *__restrict__ partial /* [chunks][rows] */)
+                                                        double *__restrict__ partial /* [chunks][part_ld] */,
+                                                        int64_t part_ld)
 {
     constexpr int VN = Vec<GT>::N;
     constexpr int GEMV_KX = GemvKx<GT>::N;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(THREADS) gemv_kernel(const GT *__restrict__ G,
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) t += wpart[w][tid];
-        partial[(int64_t)blockIdx.x * rows + r0 + tid] = t;
+        partial[(int64_t)blockIdx.x * part_ld + r0 + tid] = t;
     }
 }
 
@@ -295,7 +296,7 @@ int64_t col_splits(int64_t rows, int64_t cols)
 {
     // the narrowest chunk (fp64) gives the most CTAs per split; use it as bound
     const int64_t chunks = pf_ceil_div(cols > 0 ? cols : 1, col_chunk_width(PF_F64));
-    int64_t splits = pf_ceil_div(148 * 8, chunks);
+    int64_t splits = pf_ceil_div((int64_t)pf_sm_count() * 8, chunks);
     if (splits > MAX_SPLITS) splits = MAX_SPLITS;
     const int64_t max_by_rows = rows / 8 > 0 ? rows / 8 : 1;
     if (splits > max_by_rows) splits = max_by_rows;
@@ -381,20 +382,27 @@ extern "C" int pf_gemv(const void *G, int64_t rows, int64_t cols, int64_t ld, in
         }
         target = (double *)workspace;
     }
-    dim3 grid((unsigned)chunks, (unsigned)pf_ceil_div(rows, GEMV_ROWS));
-    PF_CHECK_ARG(grid.y <= 65535, "too many rows for one launch");
-    if (g_dtype == PF_F64) {
-        if (aligned_for_vectors<double>(G, ld))
-            gemv_kernel<double, true><<<grid, THREADS, 0, stream>>>((const double *)G, rows, cols, ld, x, target);
-        else
-            gemv_kernel<double, false><<<grid, THREADS, 0, stream>>>((const double *)G, rows, cols, ld, x, target);
-    PF_COUNT_LAUNCH();
-    } else {
-        if (aligned_for_vectors<float>(G, ld))
-            gemv_kernel<float, true><<<grid, THREADS, 0, stream>>>((const float *)G, rows, cols, ld, x, target);
-        else
-            gemv_kernel<float, false><<<grid, THREADS, 0, stream>>>((const float *)G, rows, cols, ld, x, target);
-    PF_COUNT_LAUNCH();
+    // grid.y is limited to 65535 row blocks: longer matrices go in several launches; the kernel
+    // addresses `partial` with the row count of its launch, so every launch gets the matrix
+    // and the partial array offset to its first row and the full row stride through `rows`
+    const int64_t max_rows_per_launch = (int64_t)65535 * GEMV_ROWS;
+    for (int64_t r0 = 0; r0 < rows; r0 += max_rows_per_launch) {
+        const int64_t nr = (rows - r0 < max_rows_per_launch) ? rows - r0 : max_rows_per_launch;
+        dim3 grid((unsigned)chunks, (unsigned)pf_ceil_div(nr, GEMV_ROWS));
+        const bool f64 = (g_dtype == PF_F64);
+        const char *Gr = (const char *)G + r0 * ld * (f64 ? 8 : 4);
+        if (f64) {
+            if (aligned_for_vectors<double>(G, ld))
+                gemv_kernel<double, true><<<grid, THREADS, 0, stream>>>((const double *)Gr, nr, cols, ld, x, target + r0, rows);
+            else
+                gemv_kernel<double, false><<<grid, THREADS, 0, stream>>>((const double *)Gr, nr, cols, ld, x, target + r0, rows);
+        } else {
+            if (aligned_for_vectors<float>(G, ld))
+                gemv_kernel<float, true><<<grid, THREADS, 0, stream>>>((const float *)Gr, nr, cols, ld, x, target + r0, rows);
+            else
+                gemv_kernel<float, false><<<grid, THREADS, 0, stream>>>((const float *)Gr, nr, cols, ld, x, target + r0, rows);
+        }
+        PF_COUNT_LAUNCH();
     }
     PF_CUDA_OK(cudaGetLastError());
     if (chunks > 1) {
@@ -568,7 +576,7 @@ extern "C" int pf_probe_fp64_peak(double *flops, void *stream_)
     cudaEvent_t e0, e1;
     PF_CUDA_OK(cudaEventCreate(&e0));
     PF_CUDA_OK(cudaEventCreate(&e1));
-    const int blocks = 148 * 8 * 4;
+    const int blocks = pf_sm_count() * 8 * 4;
     dfma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, 0.999999, 1e-9);
     PF_COUNT_LAUNCH();
     float best_ms = 1e30f;

@@ -13,16 +13,22 @@ import numpy as np
 import scipy.sparse as sp
 
 
-class IdentityDeriv(sp.csr_matrix):
-    """``sp.identity`` that says so: lets the simulations skip the (host-side,
-    O(nP)) sparse products with the derivative of an identity mapping."""
-
-    is_identity = True
+def is_identity_deriv(d):
+    """True only for the very objects ``IdentityMap.deriv`` hands out.  The flag is an INSTANCE
+    attribute of a plain ``csr_matrix``: scipy builds the results of ``2 * d``, ``-d``,
+    ``d @ other``, ``d[:k]`` and ``d.copy()`` as new matrices without it, so a scaled or chained
+    derivative is never mistaken for the identity."""
+    return getattr(d, "is_identity", False) is True
 
 
 @functools.lru_cache(maxsize=4)
 def _identity_deriv(n):
-    return IdentityDeriv(sp.identity(n, format="csr"))
+    d = sp.identity(n, format="csr")
+    d.is_identity = True
+    # shared between calls: make the buffers read-only so that in-place edits fail loudly
+    for a in (d.data, d.indices, d.indptr):
+        a.flags.writeable = False
+    return d
 
 
 class IdentityMap:

@@ -17,11 +17,12 @@ sharded over the ranks of ``torch.distributed`` when it is initialised
 """
 from __future__ import annotations
 
+import os
 import warnings
 
 import numpy as np
 import scipy.sparse as sp
-from scipy.sparse.linalg import LinearOperator
+from scipy.sparse.linalg import LinearOperator, aslinearoperator
 
 from ..utils import validate_active_indices, validate_string
 
@@ -154,7 +155,8 @@ class BasePFSimulation:
 
     def __init__(self, mesh, active_cells=None, store_sensitivities="ram", n_processes=1,
                  sensitivity_dtype=np.float32, engine="cuda", numba_parallel=True,
-                 survey=None, sensitivity_path="./sensitivities", comm=None, device=None,
+                 survey=None, sensitivity_path=None, counter=None, verbose=False,
+                 linear_model=None, model_map=None, G=None, comm=None, device=None,
                  **kwargs):
         if kwargs.pop("ind_active", None) is not None:
             raise TypeError("'ind_active' has been removed in SimPEG v0.24.0, "
@@ -167,7 +169,18 @@ class BasePFSimulation:
         self.engine = engine
         self.numba_parallel = bool(numba_parallel)  # accepted for API parity; unused by "cuda"
         self.survey = survey
-        self.sensitivity_path = sensitivity_path
+        # BaseSimulation.__init__ (simpeg/simulation.py:62-80): default path, counter, verbose
+        if sensitivity_path is None:
+            sensitivity_path = os.path.join(".", "sensitivity")
+        self.sensitivity_path = validate_string("sensitivity_path", sensitivity_path,
+                                                case_sensitive=True)
+        self.counter = counter          # kept for API parity (nothing on this path counts)
+        self.verbose = bool(verbose)
+        # LinearSimulation.__init__ (simpeg/simulation.py:655-668): linear_model / model_map are
+        # the generic names of rho|chi / rhoMap|chiMap; a user-supplied G replaces the kernel
+        # evaluation (uploaded to HBM on first use, see the G property)
+        self.linear_model, self.model_map = linear_model, model_map
+        self._G_source = G
         self.n_processes = n_processes
         n_cells = mesh.n_cells
         if active_cells is None:
@@ -255,18 +268,23 @@ class BasePFSimulation:
 
     @model.setter
     def model(self, value):
-        if value is not None and value is getattr(self, "_model_src", None) \
-                and not self._delete_on_model_update:
-            return                      # same array object as last time: nothing cached depends on it
-        self._model_src = value
+        """props.py:457-472: always takes the new values -- the caller may have changed the same
+        array object in place, and ``_model`` only aliases its memory for contiguous float64
+        input.  Whether the values changed matters only for the caches listed in
+        ``_delete_on_model_update`` (amplitude data); the comparison is made against a private
+        copy of the values those caches were computed for and skipped when there are none."""
         if value is not None:
             value = np.asarray(value, dtype=np.float64).reshape(-1)
-        prev = self._model
-        if value is not None and prev is not None and prev.shape == value.shape \
-                and np.array_equal(prev, value):
-            return
         self._model = value
-        for name in self._delete_on_model_update:
+        deletes = self._delete_on_model_update
+        if not deletes:
+            return
+        seen = getattr(self, "_model_seen", None)
+        if value is not None and seen is not None and seen.shape == value.shape \
+                and np.array_equal(seen, value):
+            return
+        self._model_seen = None if value is None else value.copy()
+        for name in deletes:
             if hasattr(self, name):
                 delattr(self, name)
 
@@ -496,7 +514,17 @@ class BasePFSimulation:
         releases the HBM immediately (no reference cycle).
         """
         if not hasattr(self, "_G"):
-            if self.store_sensitivities == "forward_only":
+            if self._G_source is not None:
+                # LinearSimulation(G=...) / ``sim.G = array`` (simulation.py:664-665, 684-688):
+                # the caller's matrix goes to HBM instead of being evaluated
+                source = np.asarray(self._G_source)
+                shape = (self.survey.nD, self._n_columns())
+                if source.shape != shape:
+                    raise ValueError(f"G must have shape {shape}, got {source.shape}")
+                ops = self._ops
+                ops.engine.load_G_rows(source, ops.sharding.local_rows)
+                self._G_loaded = True
+            if self.store_sensitivities == "forward_only" and self._G_source is None:
                 self._G = self._sensitivity_matrix_as_operator()
             else:
                 if not getattr(self, "_G_loaded", False):
@@ -505,6 +533,29 @@ class BasePFSimulation:
                 shape = (self.survey.nD, self._n_columns())
                 self._G = DeviceLinearOperator(shape, ops.gemv, ops.gemv_t, ops.G_to_numpy)
         return self._G
+
+    @G.setter
+    def G(self, value):
+        if hasattr(self, "_G"):
+            del self._G
+        self._G_source = value
+        self._G_loaded = False
+
+    def _jacobian(self, deriv):
+        """``getJ`` of the reference (gravity/simulation.py:318-355): ``G @ deriv`` as a dense
+        ndarray for 'ram' / 'disk' -- as long as it fits ``getJ_dense_max_bytes`` on the host and
+        one process owns every row -- and as a LinearOperator otherwise ('forward_only', sharded
+        runs, production sizes, where the matrix only exists in HBM)."""
+        G = self.G
+        nbytes = self.survey.nD * self._n_columns() * np.dtype(self.sensitivity_dtype).itemsize
+        dense = (self.store_sensitivities != "forward_only" and self._coll.world_size == 1
+                 and nbytes <= self.getJ_dense_max_bytes)
+        if not dense:
+            return G @ aslinearoperator(deriv)
+        Gh = G.to_numpy()
+        return Gh if getattr(deriv, "is_identity", False) else np.asarray(Gh @ deriv)
+
+    getJ_dense_max_bytes = 1 << 30
 
     def _warn_n_processes(self, kwargs, what):
         if "n_processes" in kwargs:

@@ -77,9 +77,10 @@ class Simulation3DIntegral(BasePFSimulation):
         return self._cols_to_host(dev.colsumsq_dev(self._local_rows_of(weights)))
 
     def getJ(self, m, f=None):
-        """gravity/simulation.py:318-355: always a LinearOperator for engine='cuda'."""
+        """gravity/simulation.py:318-355: ndarray for 'ram' / 'disk' (small enough for the host),
+        LinearOperator otherwise (see ``BasePFSimulation._jacobian``)."""
         self.model = m
-        return self.G @ aslinearoperator(self.rhoDeriv)
+        return self._jacobian(self.rhoDeriv)
 
     def Jvec(self, m, v, f=None):
         """gravity/simulation.py:357-387"""

@@ -136,7 +136,7 @@ class Simulation3DIntegral(BasePFSimulation):
             raise NotImplementedError(
                 "The `getJ` method is not yet implemented to work with `is_amplitude_data`.")
         self.model = m
-        return self.G @ aslinearoperator(self.chiDeriv)
+        return self._jacobian(self.chiDeriv)
 
     def getJtJdiag(self, m, W=None, f=None):
         """magnetics/simulation.py:346-406"""

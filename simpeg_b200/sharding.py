@@ -92,6 +92,19 @@ class ReceiverSharding:
         return self._gather_index
 
 
+    def gather_source_index_on(self, device):
+        """The gather index as a tensor on ``device`` -- cached on THIS object (one entry per
+        device), so that it lives and dies with the row layout it describes."""
+        import torch
+
+        cache = self.__dict__.setdefault("_gather_index_t", {})
+        key = str(device)
+        if key not in cache:
+            _, index = self.gather_source_index()
+            cache[key] = None if index is None else torch.from_numpy(index).to(device)
+        return cache[key]
+
+
 class Collectives:
     """Thin wrapper over ``torch.distributed`` (a no-op for a single process)."""
 
@@ -151,9 +164,7 @@ class Collectives:
         if self._dist is None:
             return local            # one process owns every row, already in global order
         m, index = sharding.gather_source_index()
-        key = (id(sharding), str(local.device))
-        if index is not None and (getattr(self, "_index_cache", None) is None or self._index_cache[0] != key):
-            self._index_cache = (key, torch.from_numpy(index).to(local.device))
+        index_t = sharding.gather_source_index_on(local.device) if index is not None else None
         if local.numel() == m:
             padded = local.contiguous()
         else:
@@ -161,4 +172,4 @@ class Collectives:
             padded[: local.numel()] = local
         gathered = torch.empty(m * self.world_size, dtype=local.dtype, device=local.device)
         self._dist.all_gather_into_tensor(gathered, padded, group=self.group)
-        return gathered[: sharding.nD] if index is None else gathered[self._index_cache[1]]
+        return gathered[: sharding.nD] if index is None else gathered[index_t]

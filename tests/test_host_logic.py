@@ -185,3 +185,75 @@ def test_receiver_sharding_rows():
     assert np.array_equal(np.sort(np.concatenate(all_rows)), np.arange(14))
     # rank 0 owns locations [0,2) of object a -> rows 0..3, and [0,2) of b -> rows 10, 11
     assert all_rows[0].tolist() == [0, 1, 2, 3, 10, 11]
+
+
+# ---------------------------------------------------------------- round-2 boundary fixes
+def test_base_simulation_keywords_are_accepted():
+    # simpeg/simulation.py:62-80 (sensitivity_path default, counter, verbose) and :655-668
+    # (linear_model, model_map) -- a reference call site must not hit a TypeError
+    sim = gravity.Simulation3DIntegral(small_mesh(), counter=None, verbose=True,
+                                       linear_model=None, model_map=None)
+    assert sim.sensitivity_path == "./sensitivity"
+    assert sim.verbose is True and sim.counter is None
+    with pytest.raises(TypeError, match="'sensitivity_path' must be a str"):
+        gravity.Simulation3DIntegral(small_mesh(), sensitivity_path=3)
+
+
+@pytest.mark.parametrize("make", [
+    lambda n: np.zeros(n, dtype=np.float32),
+    lambda n: [0.0] * n,
+    lambda n: np.zeros(2 * n)[::2],
+    lambda n: np.zeros(n),
+])
+def test_model_reassigned_after_in_place_edit_is_seen(make):
+    # props.py:457-472 always assigns; ADVICE round 1: the identity short-circuit kept stale
+    # converted copies of float32 / list / strided models
+    mesh = small_mesh()
+    sim = gravity.Simulation3DIntegral(mesh, rhoMap=maps.IdentityMap(nP=mesh.n_cells))
+    m = make(mesh.n_cells)
+    sim.model = m
+    assert np.all(sim.rho == 0.0)
+    m[0] = 2.5
+    sim.model = m
+    assert sim.rho[0] == 2.5
+
+
+def test_amplitude_caches_follow_the_model_values():
+    # magnetics/simulation.py:822-827: _ampDeriv / _gtg_diagonal die with the model
+    mesh = small_mesh()
+    sim = magnetics.Simulation3DIntegral(mesh, chiMap=maps.IdentityMap(nP=mesh.n_cells),
+                                         is_amplitude_data=True)
+    m = np.zeros(mesh.n_cells, dtype=np.float32)
+    sim.model = m
+    sim._ampDeriv = "cached"
+    sim.model = m                     # same values: cache kept
+    assert sim._ampDeriv == "cached"
+    m[3] = 1.0                        # same object, new values: cache dropped
+    sim.model = m
+    assert not hasattr(sim, "_ampDeriv")
+
+
+def test_identity_flag_does_not_survive_arithmetic():
+    d = maps.IdentityMap(nP=6).deriv(np.zeros(6))
+    assert maps.is_identity_deriv(d)
+    import scipy.sparse as sp
+
+    for other in (2 * d, -d, d @ sp.diags(np.arange(6.0)), d[:3], d.copy(), d.T):
+        assert not getattr(other, "is_identity", False)
+    with pytest.raises(ValueError):
+        d.data[0] = 2.0               # the cached matrix is shared, hence read-only
+    diag = np.arange(1.0, 7.0)
+    assert np.allclose(gravity.Simulation3DIntegral._jtj_diagonal(diag, 2 * d), 4 * diag)
+
+
+def test_gather_index_is_cached_on_the_sharding_object():
+    import torch
+
+    loc = np.zeros((5, 3))
+    s = ReceiverSharding([(loc, ["gz"]), (loc[:3], ["gz", "gzz"])], rank=0, world_size=2)
+    t = s.gather_source_index_on(torch.device("cpu"))
+    assert t is s.gather_source_index_on(torch.device("cpu"))
+    m, index = s.gather_source_index()
+    assert torch.equal(t, torch.from_numpy(index))
+    other = ReceiverSharding([(loc, ["gz"])], rank=0, world_size=2)
+    assert other.gather_source_index_on(torch.device("cpu")) is None   # equal contiguous blocks
