@@ -153,7 +153,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU baseline
-def cpu_baseline(wl, sample_rx=None, repeats=1):
+def cpu_baseline(wl, sample_rx=None, repeats=1, threads=None):
     """
     The oracle port (oracle/pf_oracle.c: C + OpenMP restatement of the reference's
     numba-parallel loops) timed on the host cores on a bounded receiver
@@ -163,6 +163,8 @@ def cpu_baseline(wl, sample_rx=None, repeats=1):
     from oracle import oracle
 
     mesh = wl["mesh"]
+    if threads:
+        oracle.set_num_threads(threads)       # torchrun exports OMP_NUM_THREADS=1: ask explicitly
     cores = oracle.num_threads()
     nC = mesh.n_cells
     if sample_rx is None:
@@ -198,15 +200,30 @@ def cpu_baseline(wl, sample_rx=None, repeats=1):
     pairs = loc.shape[0] * nC
     rng = np.random.default_rng(2)
     v, w = rng.uniform(size=sim.nP), rng.uniform(size=sim.nD)
+    try:                                       # numpy's BLAS also obeys OMP_NUM_THREADS=1 under torchrun
+        from threadpoolctl import threadpool_limits
+        blas = threadpool_limits(limits=cores)
+    except Exception:  # pragma: no cover
+        blas = None
     G @ v
     t = time.perf_counter()
     G @ v
     G.T @ w
     tprod = time.perf_counter() - t
+    if blas is not None:
+        blas.restore_original_limits()
     return {"value": pairs / best, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{done_rx} receivers (chunks of {sample_rx}) x full mesh ({nC} cells, "
                       f"{sim.nP} columns), oracle/pf_oracle.c OpenMP, {best:.2f} s",
             "jvec_jtvec_gbs": 2 * G.nbytes / tprod / 1e9, "seconds": best}
+
+
+def host_cores():
+    """Host threads this process may use (affinity mask, not OMP_NUM_THREADS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -215,12 +232,13 @@ def run_reference(args):
     if rank != 0:
         return
     wl = make_workload(args.workload, args.gpus, args.receivers_per_gpu)
+    threads = host_cores()                    # all the host threads this process may use
     for _ in range(max(args.warmup, 1)):
-        cpu_baseline(wl, sample_rx=8, repeats=0)
+        cpu_baseline(wl, sample_rx=8, repeats=0, threads=threads)
     times, last = [], None
     for _ in range(args.steps):
         t = time.perf_counter()
-        last = cpu_baseline(wl)
+        last = cpu_baseline(wl, threads=threads)
         times.append(time.perf_counter() - t)
     out = {
         "impl": "reference", "metric": METRIC, "value": last["value"], "unit": UNIT,
@@ -252,6 +270,297 @@ def workload_config(wl, n_gpus):
     }
 
 
+# --------------------------------------------------------------------------- parity (checker)
+PARITY_TOL = 1e-9          # north_star: relative 1e-9 in fp64, norm-wise (max|d| / max|ref|)
+
+
+def _rel(a, b):
+    den = float(np.max(np.abs(b))) if b.size else 0.0
+    return float(np.max(np.abs(np.asarray(a) - b)) / den) if den > 0 else float(np.max(np.abs(a), initial=0.0))
+
+
+def port_rows(physics, nodes, cell_nodes, locations, components, b0, model_type, threads):
+    """Rows of G for a few receivers from the CPU port (oracle/pf_oracle.c) -- the checker."""
+    from oracle import oracle
+
+    oracle.set_num_threads(max(1, int(threads)))
+    sim = oracle.OracleSimulation(physics, nodes, cell_nodes, [(locations, components)], b0=b0,
+                                  model_type=model_type, backend="c", parallel=True)
+    return sim.sensitivity_matrix()
+
+
+def sample_positions(n_local_rx, n_sample):
+    n = min(n_sample, n_local_rx)
+    return np.unique(np.linspace(0, n_local_rx - 1, n).round().astype(np.int64)) if n else np.zeros(0, np.int64)
+
+
+def stored_g_parity(wl, sim, coll, b0, n_sample, torch, dist):
+    """
+    Compare, OUTSIDE the timed region, the GPU results with the CPU port on a receiver sample of
+    EVERY rank: the rank-local rows of G, Jvec on those rows, and the all-reduced Jtvec /
+    column norms for a vector that is non-zero on the sample rows of all ranks only (so that the
+    exact answer is the sum over ranks of the port's G_s^T w_s).  Returns the parity dict; the
+    maxima are taken over ranks.
+    """
+    eng, sh = sim._dev, sim._sharding
+    C = len(wl["components"])
+    nP, nD = eng.nP, sh.nD
+    world, rank = coll.world_size, coll.rank
+    loc_local = sh.local_receiver_list[0][0]
+    pos = sample_positions(loc_local.shape[0], n_sample)
+    rows_local = (pos[:, None] * C + np.arange(C)[None, :]).reshape(-1)
+    rows_global = sh.local_rows[rows_local]
+    nodes, cell_nodes = sim._get_active_nodes()
+    Gs = port_rows(wl["physics"], nodes, cell_nodes, loc_local[pos], wl["components"], b0,
+                   wl["model_type"], max(1, host_cores() // world))
+    # rows of G
+    Gd = eng.G[torch.from_numpy(rows_local).to(eng.device), :nP].double().cpu().numpy()
+    g_row = float(np.max(np.max(np.abs(Gd - Gs), axis=1) / np.max(np.abs(Gs), axis=1)))
+    # Jvec on the sample rows (every rank holds the gathered vector)
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1.0, 1.0, nP)
+    full = coll.all_gather_rows(eng.gemv_dev(eng.to_device(x)), sh)
+    jvec = _rel(full[torch.from_numpy(rows_global).to(eng.device)].cpu().numpy(), Gs @ x)
+    # Jtvec / diag with weights living on the sample rows of all ranks
+    w = np.zeros(nD)
+    for r in range(world):
+        rr = sh.rows_of_rank(r)
+        n_loc_r = rr.size // C
+        pr = sample_positions(n_loc_r, n_sample)
+        w[rr[(pr[:, None] * C + np.arange(C)[None, :]).reshape(-1)]] = 1.0
+    w *= np.random.default_rng(12).uniform(0.5, 1.5, nD)
+    w_local = sim._local_rows_of(w)
+    z = coll.all_reduce_sum(eng.gemv_t_dev(w_local)).cpu().numpy()
+    d = coll.all_reduce_sum(eng.colsumsq_dev(w_local)).cpu().numpy()
+    ws = w[rows_global]
+    ref = torch.from_numpy(np.stack([Gs.T @ ws, np.einsum("i,ij,ij->j", ws, Gs, Gs)])).to(eng.device)
+    if world > 1:
+        dist.all_reduce(ref)          # transport for the checker's partial sums only
+    ref = ref.cpu().numpy()
+    vals = torch.tensor([g_row, jvec, _rel(z, ref[0]), _rel(d, ref[1])], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    g_row, jvec, jtvec, diag = (float(v) for v in vals.cpu())
+    return {"G_rowwise_max": g_row, "jvec": jvec, "jtvec": jtvec, "diag": diag, "tol": PARITY_TOL,
+            "n_rx": int(pos.size) * world, "ranks": world, "against": "oracle/pf_oracle.c (port)",
+            "ok": bool(max(g_row, jvec, jtvec, diag) <= PARITY_TOL)}
+
+
+# --------------------------------------------------------------------------- measured DRAM traffic
+def measured_traffic(kernel_name, algorithmic_bytes):
+    """DRAM bytes per launch of the dominant kernel from THIS round's committed ncu capture
+    (profiles/r2_traffic.json, written by scripts/ncu_traffic.py from `ncu --set full`), scaled by
+    the algorithmic bytes of this run; None when the capture does not cover the kernel."""
+    try:
+        table = json.load(open(ROOT / "profiles" / "r2_traffic.json"))
+    except (OSError, ValueError):
+        return None, "no ncu capture committed for this round"
+    for entry in table.get("kernels", []):
+        if entry["match"] in kernel_name:
+            ratio = entry["dram_bytes"] / entry["algorithmic_bytes"]
+            return ratio * algorithmic_bytes, (f"dram__bytes_read+write = {ratio:.4f} x algorithmic bytes in "
+                                               f"{entry['source']}")
+    return None, "kernel not in profiles/r2_traffic.json"
+
+
+def dev_ms(torch, fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = np.inf
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+# --------------------------------------------------------------------------- other BASELINE configs
+def flop_eq_per_pair(n_nodes, n_cells):
+    return FLOP_EQ_PER_NODE * n_nodes / n_cells + FLOP_EQ_PER_CELL
+
+
+def baseline_configs(torch, fp64_peak, hbm_peak):
+    """
+    One compact entry per BASELINE.json config, each at its per-GPU size, through the public API,
+    each with its own throughput, roofline fraction and a parity number against the CPU port on a
+    receiver sample (<= ~2 s of GPU time per entry).  cfg4 is the headline workload itself.
+    """
+    import scipy.sparse as sp
+
+    from simpeg_b200 import maps
+    from simpeg_b200.meshes import TensorMesh, synthetic_octree
+    from simpeg_b200.potential_fields import gravity, magnetics
+    from simpeg_b200.utils import dip_azimuth2cartesian
+
+    threads = host_cores()
+    out = {}
+
+    def release():
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def sync_time(fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t, r
+
+    # ---- cfg1: gravity gz, 40x40x20, 21x21 receivers, stored G (the reference's CPU-runnable case)
+    wl = make_workload("cfg1", 1, None)
+    survey = make_survey(wl, wl["locations"])
+    sim = make_simulation(wl, survey)
+    nC = wl["mesh"].n_cells
+    rho = np.random.default_rng(3).uniform(-0.5, 0.5, nC)
+    sim.G
+    t_build = dev_ms(torch, sim._dev.build_G)
+    pos = sample_positions(wl["n_rx"], 16)
+    Gs = port_rows("gravity", wl["mesh"].nodes, wl["mesh"].cell_nodes, wl["locations"][pos], ["gz"], None,
+                   "scalar", threads)
+    J = sim.getJ(rho)
+    out["cfg1"] = {
+        "what": "gravity gz forward + getJ, TensorMesh 40x40x20, 441 receivers, store='ram' (full config)",
+        "build_pairs_s": wl["n_rx"] * nC / t_build * 1e3, "ms_build": t_build,
+        "kernel": sim._dev.describe("store"),
+        "frac_fp64": wl["n_rx"] * nC / t_build * 1e3 * flop_eq_per_pair(wl["mesh"].n_nodes, nC) / fp64_peak,
+        "parity": max(_rel(np.asarray(J)[pos], Gs), _rel(sim.dpred(rho)[pos], Gs @ rho)),
+        "getJ_is_ndarray": isinstance(J, np.ndarray),
+    }
+    del sim, J
+    release()
+
+    # ---- cfg2-shard: gravity 6 tensor components + gz, 100x100x50, 1250 receivers (35 GB G)
+    wl = make_workload("cfg2-shard", 1, None)
+    survey = make_survey(wl, wl["locations"])
+    sim = make_simulation(wl, survey)
+    eng = sim._dev
+    nC, C = wl["mesh"].n_cells, len(wl["components"])
+    sim.G
+    t_build = dev_ms(torch, eng.build_G)
+    g_bytes = eng.n_rows * nC * 8
+    xd = eng.to_device(np.random.default_rng(4).uniform(-1, 1, nC))
+    wd = eng.to_device(np.random.default_rng(5).uniform(0, 1, eng.n_rows))
+    t_prod = dev_ms(torch, lambda: (eng.gemv_dev(xd), eng.gemv_t_dev(wd)))
+    pos = sample_positions(wl["n_rx"], 4)
+    rows = (pos[:, None] * C + np.arange(C)[None, :]).reshape(-1)
+    Gs = port_rows("gravity", wl["mesh"].nodes, wl["mesh"].cell_nodes, wl["locations"][pos],
+                   wl["components"], None, "scalar", threads)
+    Gd = eng.G[torch.from_numpy(rows).to(eng.device), :nC].cpu().numpy()
+    out["cfg2-shard"] = {
+        "what": "gravity gxx,gxy,gxz,gyy,gyz,gzz,gz, TensorMesh 100x100x50, 1250 receivers per GPU "
+                "(8750 rows, 35 GB fp64 G): one-pass build + Jvec/Jtvec",
+        "build_pairs_s": wl["n_rx"] * nC / t_build * 1e3, "ms_build": t_build,
+        "kernel": eng.describe("store"),
+        "frac_fp64": wl["n_rx"] * nC / t_build * 1e3 * flop_eq_per_pair(wl["mesh"].n_nodes, nC) / fp64_peak,
+        "jvec_jtvec_gbs": 2 * g_bytes / t_prod / 1e6, "frac_hbm": 2 * g_bytes / t_prod / 1e6 / hbm_peak,
+        "parity": float(np.max(np.max(np.abs(Gd - Gs), axis=1) / np.max(np.abs(Gs), axis=1))),
+    }
+    del xd, wd, sim, eng, Gd
+    release()
+
+    # ---- cfg3-shard: TMI scalar forward_only on 200x200x100 (4 M cells), 5000 receivers
+    n_rx = 5000
+    mesh = TensorMesh([np.full(200, 25.0), np.full(200, 25.0), np.full(100, 25.0)], "CCN")
+    side = int(np.ceil(np.sqrt(n_rx)))
+    xs = np.linspace(-2500.0, 2500.0, side)
+    X, Y = np.meshgrid(xs, xs)
+    loc = np.c_[X.ravel(), Y.ravel(), np.full(X.size, 30.0)][:n_rx]
+    rx = magnetics.receivers.Point(loc, components="tmi")
+    src = magnetics.sources.UniformBackgroundField([rx], 50000.0, 60.0, 250.0)
+    survey = magnetics.survey.Survey(src)
+    nC = mesh.n_cells
+    rng = np.random.default_rng(4)
+    chi = rng.uniform(0.0, 0.05, nC)
+    sim = magnetics.Simulation3DIntegral(mesh, survey=survey, chiMap=maps.IdentityMap(nP=nC),
+                                         store_sensitivities="forward_only")
+    pos = sample_positions(n_rx, 4)
+    b0 = 50000.0 * dip_azimuth2cartesian(60.0, 250.0).squeeze()
+    Gs = port_rows("magnetics", mesh.nodes, mesh.cell_nodes, loc[pos], ["tmi"], b0, "scalar", threads)
+    v = np.zeros(n_rx)
+    v[pos] = rng.uniform(0.5, 1.5, pos.size)
+    sim.dpred(chi)                                                   # warm-up (plan, uploads)
+    t_fwd, d = sync_time(lambda: sim.dpred(chi))
+    t_jt, jt = sync_time(lambda: sim.Jtvec(chi, v))
+    t_dg, dg = sync_time(lambda: sim.getJtJdiag(chi, W=sp.diags(np.sqrt(v))))
+    pairs = n_rx * nC
+    fe = flop_eq_per_pair(mesh.n_nodes, nC)
+    out["cfg3-shard"] = {
+        "what": "magnetic TMI scalar, store_sensitivities='forward_only', TensorMesh 200x200x100 (4 M cells), "
+                "5000 receivers per GPU; public API with numpy vectors (wall clock)",
+        "dpred_pairs_s": pairs / t_fwd, "jtvec_pairs_s": pairs / t_jt, "getJtJdiag_pairs_s": pairs / t_dg,
+        "kernels": {"dpred": sim._dev.describe("forward"), "jtvec": sim._dev.describe("gtv"),
+                    "diag": sim._dev.describe("diag")},
+        "frac_fp64": {"dpred": pairs / t_fwd * fe / fp64_peak, "jtvec": pairs / t_jt * fe / fp64_peak,
+                      "diag": pairs / t_dg * fe / fp64_peak},
+        "parity": max(_rel(d[pos], Gs @ chi), _rel(jt, Gs.T @ v[pos]),
+                      _rel(dg, np.einsum("i,ij,ij->j", v[pos], Gs, Gs))),
+    }
+    del Gs, sim
+    release()
+
+    # ---- cfg5-shard: gravity gz on an octree below topography, 1.96 M cells, 6250 receivers (98 GB G)
+    def topo(x, y):
+        return 50.0 * np.exp(-0.5 * ((x / 100.0) ** 2 + (y / 100.0) ** 2)) - 50.0
+
+    t0 = time.perf_counter()
+    mesh = synthetic_octree((140, 140, 12), 10.0, levels=3, topo=topo)
+    t_mesh = time.perf_counter() - t0
+    n_rx = 6250
+    rng = np.random.default_rng(6)
+    half = 140 * 40.0 / 2
+    xy = rng.uniform(-half, half, (n_rx, 2))
+    loc = np.c_[xy, topo(xy[:, 0], xy[:, 1]) + 5.0]
+    rx = gravity.receivers.Point(loc, components=["gz"])
+    survey = gravity.survey.Survey(gravity.sources.SourceField([rx]))
+    nC = mesh.n_cells
+    sim = gravity.Simulation3DIntegral(mesh, survey=survey, rhoMap=maps.IdentityMap(nP=nC),
+                                       sensitivity_dtype=np.float64)
+    t_plan, eng = sync_time(lambda: sim._dev)          # generic tile plan (host, native) + uploads
+    t_build, _ = sync_time(lambda: sim.G)
+    t_build2 = dev_ms(torch, eng.build_G, reps=2) * 1e-3
+    wts = rng.uniform(0.5, 1.5, n_rx)
+    m = rng.uniform(-0.5, 0.5, nC)
+    sim.getJtJdiag(m, W=sp.diags(wts))
+    t_diag, diag = sync_time(lambda: sim.getJtJdiag(m, W=sp.diags(wts * 1.0001)))
+    g_bytes = n_rx * nC * 8
+    # well-posed Gauss-Newton system: gradient of the misfit of a synthetic anomaly
+    from simpeg_b200.gauss_newton import DeviceGaussNewtonCG
+
+    m_true = np.zeros(nC)
+    cc = mesh.cell_centers
+    m_true[np.linalg.norm(cc - np.array([0.0, 0.0, -150.0]), axis=1) < 120.0] = 0.5
+    grad = 2.0 * sim.Jtvec(m, wts**2 * (sim.dpred(m) - sim.dpred(m_true)))   # misfit gradient at m
+    solver = DeviceGaussNewtonCG(sim, data_weights=wts, reg_hessian=np.ones(nC), beta=1e-3 * float(diag.mean()),
+                                 cg_maxiter=10, cg_rtol=0.0)
+    solver.set_model(m)
+    solver.jacobi_preconditioner()
+    solver.find_search_direction(grad)
+    t_cg, _ = sync_time(lambda: solver.find_search_direction(grad))
+    pos = sample_positions(n_rx, 4)
+    nodes, cell_nodes = sim._get_active_nodes()
+    Gs = port_rows("gravity", nodes, cell_nodes, loc[pos], ["gz"], None, "scalar", threads)
+    Gd = eng.G[torch.from_numpy(pos).to(eng.device), :nC].cpu().numpy()
+    out["cfg5-shard"] = {
+        "what": "gravity gz, synthetic octree below topography (1.96 M active cells, hanging nodes), 6250 "
+                "receivers per GPU (98 GB fp64 G): build, getJtJdiag, device Gauss-Newton CG (public API)",
+        "cells": nC, "mesh_s": t_mesh, "plan_upload_s": t_plan, "tiles": int(eng.host_plan.n_tiles),
+        "build_pairs_s": n_rx * nC / t_build2, "ms_build": 1e3 * t_build2, "first_build_s": t_build,
+        "kernel": eng.describe("store"),
+        "frac_fp64": n_rx * nC / t_build2 * flop_eq_per_pair(nodes.shape[0], nC) / fp64_peak,
+        "getJtJdiag_gbs": g_bytes / t_diag / 1e9, "frac_hbm_getJtJdiag": g_bytes / t_diag / 1e9 / hbm_peak,
+        "cg_ms_per_iteration": 1e3 * t_cg / max(solver.cg_count, 1),
+        "cg_jvec_jtvec_gbs": 2 * g_bytes * solver.cg_count / t_cg / 1e9,
+        "cg_rel_residual": float(solver.cg_rel_resid),
+        "parity": float(np.max(np.max(np.abs(Gd - Gs), axis=1) / np.max(np.abs(Gs), axis=1))),
+    }
+    del solver, sim, eng, Gd
+    release()
+    return out
+
+
 # --------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
     import torch
@@ -277,6 +586,7 @@ def run_cuda(args):
     nC = wl["mesh"].n_cells
     rng = np.random.default_rng(5)
     survey = make_survey(wl, wl["locations"])
+    b0 = np.asarray(survey.source_field.b0) if wl["physics"] == "magnetics" else None
 
     def barrier():
         if world > 1:
@@ -304,18 +614,26 @@ def run_cuda(args):
 
     x_dev = eng.to_device(v_host)
     w_local = sim._local_rows_of(w_host)
+    ops = sim._ops
+    token = torch.zeros(1, dtype=torch.float64, device=eng.device)
 
     def step(timers=None):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        # events: build | rank alignment | Jvec kernel | all-gather | Jtvec kernel + all-reduce.
+        # The alignment is a one-element all-reduce ON THE DEVICE (no host sync): it makes every
+        # rank wait for the slowest build, so that build skew is reported as `ms_skew` instead
+        # of leaking into the Jvec timer.
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
         eng.build_G()
         ev[1].record()
-        y = eng.gemv_dev(x_dev)                          # Jvec: local rows ...
-        full = coll.all_gather_rows(y, sim._sharding)    # ... gathered on every rank
+        coll.all_reduce_sum(token)
         ev[2].record()
-        z = eng.gemv_t_dev(w_local)                      # Jtvec: partial columns ...
-        coll.all_reduce_sum(z)                           # ... summed over ranks
+        y = eng.gemv_dev(x_dev)                          # Jvec: local rows ...
         ev[3].record()
+        full = coll.all_gather_rows(y, sim._sharding)    # ... gathered on every rank
+        ev[4].record()
+        z = ops.gemv_t_allreduce_dev(w_local)            # Jtvec: column partials summed over ranks
+        ev[5].record()
         if timers is not None:
             timers.append(ev)
         return full, z
@@ -336,13 +654,22 @@ def run_cuda(args):
     barrier()
     launches = launch_count() - launches0
     clocks = sampler.stop()
-    t_total = max_over_ranks(e_start.elapsed_time(e_stop)) * 1e-3
-    t_build = max_over_ranks(sum(e[0].elapsed_time(e[1]) for e in timers)) * 1e-3
-    t_jvec = max_over_ranks(sum(e[1].elapsed_time(e[2]) for e in timers)) * 1e-3
-    t_jtvec = max_over_ranks(sum(e[2].elapsed_time(e[3]) for e in timers)) * 1e-3
     K = args.steps
+
+    def part(i, j):
+        return max_over_ranks(sum(e[i].elapsed_time(e[j]) for e in timers)) * 1e-3
+
+    t_total = max_over_ranks(e_start.elapsed_time(e_stop)) * 1e-3
+    t_build, t_skew = part(0, 1), part(1, 2)
+    t_gemv, t_gather, t_jtvec = part(2, 3), part(3, 4), part(4, 5)
+    t_jvec = t_gemv + t_gather
     value = pairs_total * K / t_build
     prod_gbs = 2 * g_bytes_total * K / (t_jvec + t_jtvec) / 1e9
+    # the Jtvec kernel alone (no collective), for the cost of the all-reduce inside ms_jtvec
+    t_gemv_t_alone = max_over_ranks(dev_ms(torch, lambda: eng.gemv_t_dev(w_local))) * 1e-3
+
+    # ---- parity against the CPU port on a receiver sample of every rank (not timed) --------
+    parity = stored_g_parity(wl, sim, coll, b0, args.parity_rx, torch, dist)
 
     # ---- the other sinks of the path (matrix-free forward / G^T v / diag, weighted column
     #      norms of the stored G), timed on the device on a receiver subsample ------------
@@ -352,46 +679,43 @@ def run_cuda(args):
 
         n_sub = min(256, eng.n_rows // len(wl["components"]))
         sub = CudaEngine(wl["physics"], None, None, [(wl["locations"][:n_sub], wl["components"])],
-                         b0=np.asarray(survey.source_field.b0) if wl["physics"] == "magnetics" else None,
-                         model_type=wl["model_type"], plan=eng.host_plan)
+                         b0=b0, model_type=wl["model_type"], plan=eng.host_plan)
         sub_pairs = n_sub * nC
         ws = sub.to_device(w_host[: sub.n_rows])
-
-        def dev_ms(fn, reps=3):
-            fn()
-            torch.cuda.synchronize()
-            best = np.inf
-            for _ in range(reps):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                b.record()
-                torch.cuda.synchronize()
-                best = min(best, a.elapsed_time(b))
-            return best
-
         extras = {
             "sample": f"{n_sub} receivers x full mesh, device-resident vectors, best of 3",
-            "forward_only_dpred_pairs_s": sub_pairs / dev_ms(lambda: sub.forward_dev(x_dev)) * 1e3,
-            "forward_only_gt_dot_v_pairs_s": sub_pairs / dev_ms(lambda: sub.gt_dot_v_dev(ws)) * 1e3,
-            "forward_only_gtg_diag_pairs_s": sub_pairs / dev_ms(lambda: sub.gtg_diag_dev(ws)) * 1e3,
-            "stored_G_colsumsq_gbs": g_bytes_local / dev_ms(lambda: eng.colsumsq_dev(w_local)) / 1e6,
+            "forward_only_dpred_pairs_s": sub_pairs / dev_ms(torch, lambda: sub.forward_dev(x_dev)) * 1e3,
+            "forward_only_gt_dot_v_pairs_s": sub_pairs / dev_ms(torch, lambda: sub.gt_dot_v_dev(ws)) * 1e3,
+            "forward_only_gtg_diag_pairs_s": sub_pairs / dev_ms(torch, lambda: sub.gtg_diag_dev(ws)) * 1e3,
+            "stored_G_colsumsq_gbs": g_bytes_local / dev_ms(torch, lambda: eng.colsumsq_dev(w_local)) / 1e6,
+            "kernels": {"forward": sub.describe("forward"), "gt_dot_v": sub.describe("gtv"),
+                        "gtg_diag": sub.describe("diag")},
         }
         del sub, ws
 
     # ---- device-resident Gauss-Newton CG: 5 iterations of
     #      q = 2 G^T W^2 G p + beta p with all vectors in HBM, one all-reduce per iteration;
-    #      host vectors only for the gradient in and the step out (inside the timing) ---------
+    #      host vectors only for the gradient in and the step out (inside the timing).
+    #      The system is a real Gauss-Newton step: the gradient is that of the misfit of a
+    #      synthetic anomaly, g = -2 J^T W^2 (d_obs - d(m)), so it lies in range(J^T) and the
+    #      preconditioned CG residual must go DOWN (checked below) -------------------------
     from simpeg_b200.gauss_newton import DeviceGaussNewtonCG
 
     cg_iters = 5
     jtj = sim.getJtJdiag(m_host)                          # stored-G column norms (not timed)
-    solver = DeviceGaussNewtonCG(sim, data_weights=np.ones(nD), reg_hessian=np.ones(nP),
-                                 beta=1e-3 * float(jtj.mean()), cg_maxiter=cg_iters, cg_rtol=0.0,
+    cc = wl["mesh"].cell_centers
+    m_true = np.zeros(nP)
+    blob = np.linalg.norm(cc - np.array([0.0, 0.0, -0.4 * wl["shape"][2] * wl["h"]]), axis=1) \
+        < 0.15 * wl["shape"][0] * wl["h"]
+    m_true[:nC][blob] = 0.05                              # first column block (x component / scalar)
+    d_obs = sim.dpred(m_true)
+    wd = np.full(nD, 1.0 / max(float(np.abs(d_obs).max()) * 0.02, 1e-30))   # 2 % of the peak anomaly
+    g_host = 2.0 * sim.Jtvec(m_host, wd**2 * (sim.dpred(m_host) - d_obs))   # gradient of the misfit at m_host
+    solver = DeviceGaussNewtonCG(sim, data_weights=wd, reg_hessian=np.ones(nP),
+                                 beta=1e-3 * float((wd[0] ** 2) * jtj.mean()), cg_maxiter=cg_iters, cg_rtol=0.0,
                                  cg_atol=0.0)
     solver.set_model(m_host)
     solver.jacobi_preconditioner()                        # UpdatePreconditioner (cached diagonal)
-    g_host = rng.uniform(-1.0, 1.0, nP)
     solver.find_search_direction(g_host)                  # warm-up
     cg_t = []
     for _ in range(2):
@@ -403,13 +727,16 @@ def run_cuda(args):
     cg_s = float(np.mean(cg_t))
     cg = {"iterations": int(solver.cg_count), "ms_per_iteration": 1e3 * cg_s / max(solver.cg_count, 1),
           "jvec_jtvec_gbs": 2 * g_bytes_total * solver.cg_count / cg_s / 1e9,
-          "rel_residual": float(solver.cg_rel_resid), "checksum": float(np.sum(cg_step)),
-          "what": "DeviceGaussNewtonCG.find_search_direction: gradient H2D, 5 x (gemv, row weights, "
-                  "gemv_t, all-reduce, fused vector kernels), step D2H; wall clock, max over ranks"}
+          "rel_residual": float(solver.cg_rel_resid), "residual_decreased": bool(solver.cg_rel_resid < 1.0),
+          "checksum": float(np.sum(cg_step)),
+          "what": "DeviceGaussNewtonCG.find_search_direction on g = -2 J^T W^2 r of a synthetic anomaly: "
+                  "gradient H2D, 5 x (gemv, row weights, gemv_t + all-reduce, fused vector kernels), step "
+                  "D2H; wall clock, max over ranks"}
     del solver
+    kernel_build = eng.describe("store")
 
     # ---- end to end through the public API, host buffers in and out -------------
-    del sim, eng, x_dev, w_local, step, timers
+    del sim, eng, x_dev, w_local, step, timers, ops
     gc.collect()
     torch.cuda.empty_cache()
     e2e_build, e2e_prod = [], []
@@ -443,11 +770,6 @@ def run_cuda(args):
     e2e_value = pairs_total / float(np.mean(e2e_build))
     e2e_prod_gbs = 2 * g_bytes_total / float(np.mean(e2e_prod)) / 1e9
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     try:
         peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
@@ -455,37 +777,51 @@ def run_cuda(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+
+    configs = None
+    if world == 1 and args.configs:
+        configs = baseline_configs(torch, fp64_peak, hbm_peak)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        if not parity["ok"]:
+            sys.exit(3)
+        return
+
     n_nodes = wl["mesh"].n_nodes
-    flop_eq_per_pair = FLOP_EQ_PER_NODE * n_nodes / nC + FLOP_EQ_PER_CELL
-    build_tflops = (pairs_local * K / t_build) * flop_eq_per_pair / 1e12
+    fe_pair = flop_eq_per_pair(n_nodes, nC)
+    build_tflops = (pairs_local * K / t_build) * fe_pair / 1e12
+    traffic_b, traffic_b_src = measured_traffic(kernel_build, g_bytes_local)
+    traffic_p, traffic_p_src = measured_traffic("gemv_kernel", g_bytes_local)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "g_storage": args.g_dtype,
         "config": workload_config(wl, world),
-        "ms_build": 1e3 * t_build / K, "ms_jvec": 1e3 * t_jvec / K, "ms_jtvec": 1e3 * t_jtvec / K,
+        "ms_build": 1e3 * t_build / K, "ms_skew": 1e3 * t_skew / K,
+        "ms_jvec": 1e3 * t_jvec / K, "ms_jvec_kernel": 1e3 * t_gemv / K, "ms_allgather": 1e3 * t_gather / K,
+        "ms_jtvec": 1e3 * t_jtvec / K, "ms_jtvec_kernel_alone": 1e3 * t_gemv_t_alone,
+        "ms_allreduce_exposed": 1e3 * (t_jtvec / K - t_gemv_t_alone),
         "products": {"metric": "Jvec+Jtvec GB/s", "jvec_jtvec_gbs": prod_gbs,
-                     "frac_of_hbm": prod_gbs / (hbm_peak * world), "G_bytes": g_bytes_total},
+                     "frac_of_hbm": prod_gbs / (hbm_peak * world), "G_bytes": g_bytes_total,
+                     "per_gpu_gbs": prod_gbs / world},
+        "parity": parity,
         "roofline": {
-            "kernel": "pf_march_kernel<12, PROG_TMI_VECTOR, SINK_STORE, double, 4> (G build)", "bound": "fp64",
+            "kernel": kernel_build + " (G build)", "bound": "fp64",
             "achieved": build_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
             "frac": build_tflops / (fp64_peak / 1e12),
-            # ncu (profiles/r1g_kernels_summary.md): 7.135 GB written + 0.099 GB read for a
-            # 7.104 GB block of G -> DRAM bytes per launch = 1.0183 x the block it writes
-            "traffic": 1.0183 * g_bytes_local,
-            "note": f"algorithmic flop-eq/pair = 339*nN/nC + 64 = {flop_eq_per_pair:.1f} (SURVEY 8(d)); "
-                    "peak = DFMA probe measured in this run (pf_probe_fp64_peak); per GPU; "
-                    "ncu: FP64 pipe 58-64 % busy (the kernel issues ~260 FP64 instructions per pair)",
+            "traffic": traffic_b, "traffic_source": traffic_b_src,
+            "note": f"algorithmic flop-eq/pair = 339*nN/nC + 64 = {fe_pair:.1f} (SURVEY 8(d)); "
+                    "peak = DFMA probe measured in this run (pf_probe_fp64_peak); per GPU",
         },
         "roofline_products": {
-            "kernel": "gemv_kernel<double> + column_kernel<double,0> (Jvec + Jtvec)", "bound": "hbm",
+            "kernel": "gemv_kernel + column_kernel (Jvec + Jtvec)", "bound": "hbm",
             "achieved": g_bytes_local * 2 * K / (t_jvec + t_jtvec) / 1e9, "peak": hbm_peak,
             "unit": "GB/s", "frac": g_bytes_local * 2 * K / (t_jvec + t_jtvec) / 1e9 / hbm_peak,
-            # ncu: 7.128 GB (gemv) / 7.118 GB (gemv_t) DRAM traffic for a 7.104 GB block
-            "traffic": 1.0034 * g_bytes_local,
-            "note": f"algorithmic bytes = rows*cols*8 per product, per GPU; traffic = DRAM bytes per "
-                    f"launch scaled from the ncu capture; peak = {hbm_src}",
+            "traffic": traffic_p, "traffic_source": traffic_p_src,
+            "note": f"algorithmic bytes = rows*cols*{g_item} per product, per GPU; peak = {hbm_src}",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "jvec_jtvec_gbs": e2e_prod_gbs,
@@ -496,11 +832,17 @@ def run_cuda(args):
         "gpu_launches": int(launches), "clocks": clocks, "other_sinks": extras,
         "gauss_newton_cg": cg,
     }
+    if configs is not None:
+        out["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = {k: v for k, v in cpu_baseline(wl).items() if k != "seconds"}
+        out["cpu_baseline"] = {k: v for k, v in cpu_baseline(wl, threads=host_cores()).items() if k != "seconds"}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    bad = [k for k, v in (configs or {}).items() if not v["parity"] <= PARITY_TOL]
+    if not parity["ok"] or bad:
+        sys.stderr.write(f"PARITY FAILURE: {parity} {bad}\n")
+        sys.exit(3)
 
 
 def main():
@@ -513,6 +855,10 @@ def main():
     ap.add_argument("--receivers-per-gpu", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="skip the per-BASELINE-config block (cfg1, cfg2-shard, cfg3-shard, cfg5-shard; N=1 only)")
+    ap.add_argument("--parity-rx", type=int, default=8,
+                    help="receivers per rank checked against the CPU port after the timed loop")
     ap.add_argument("--g-dtype", default="f64", choices=["f64", "f32"],
                     help="storage type of G (sensitivity_dtype); BASELINE.json asks for fp64")
     args = ap.parse_args()

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 4
+#define PF_ABI_VERSION 5
 
 typedef enum {
     PF_OK = 0,
@@ -140,6 +140,11 @@ int64_t pf_launch_count(void);
  * and the output planes fit), so that the tile arrays of the plan are not needed for
  * pf_build_G (forward == 0) / pf_forward (forward != 0); 0 otherwise. */
 int pf_job_uses_marching(const pf_plan *plan, const pf_job *job, int forward);
+
+/* Names of the kernels (template instantiations) the passes of a job launch for a sink
+ * (0 = store G, 1 = forward, 2 = G^T v, 3 = diag), joined by " + ", written to buf (NUL-terminated,
+ * truncated at a kernel boundary): the label bench.py reports as roofline.kernel. */
+int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int g_dtype, char *buf, int64_t len);
 
 /* number of columns of G for a job: nC (gravity, scalar) or 3 nC (vector) */
 int64_t pf_job_columns(const pf_plan *plan, const pf_job *job);

@@ -15,7 +15,7 @@ import os
 LIB_PATH = Path(os.environ.get("PF_CUDA_LIB", Path(__file__).resolve().parent / "libpf_cuda.so"))
 
 PF_MAX_COMPONENTS = 16
-PF_ABI_VERSION = 4
+PF_ABI_VERSION = 5
 PF_F64, PF_F32 = 0, 1
 PF_GRAVITY, PF_MAGNETICS = 0, 1
 
@@ -35,6 +35,7 @@ MAGNETIC_COMPONENTS = {
 # every symbol declared in include/pf_cuda.h
 EXPORTED_SYMBOLS = (
     "pf_abi_version", "pf_last_error", "pf_launch_count", "pf_job_uses_marching", "pf_job_columns",
+    "pf_describe",
     "pf_build_G",
     "pf_forward_workspace_bytes", "pf_forward",
     "pf_gt_dot_v_workspace_bytes", "pf_gt_dot_v",
@@ -108,6 +109,7 @@ def load_library() -> ctypes.CDLL:
         "pf_launch_count": (i64, []),
         "pf_job_uses_marching": (i32, [PP, JP, i32]),
         "pf_job_columns": (i64, [PP, JP]),
+        "pf_describe": (i32, [PP, JP, i32, i32, ctypes.c_char_p, i64]),
         "pf_build_G": (i32, [PP, JP, vp, i64, i32, vp]),
         "pf_forward_workspace_bytes": (i64, [PP, JP]),
         "pf_forward": (i32, [PP, JP, vp, vp, vp, i64, vp]),

@@ -1463,6 +1463,66 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
 
 }  // namespace
 
+
+namespace {
+const char *prog_name(int prog)
+{
+    switch (prog) {
+    case PROG_TMI_SCALAR: return "PROG_TMI_SCALAR";
+    case PROG_TMI_VECTOR: return "PROG_TMI_VECTOR";
+    case PROG_ALL6: return "PROG_ALL6";
+    default: return "PROG_GENERIC";
+    }
+}
+const char *sink_name(int sink)
+{
+    switch (sink) {
+    case SINK_STORE: return "SINK_STORE";
+    case SINK_FORWARD: return "SINK_FORWARD";
+    case SINK_GTV: return "SINK_GTV";
+    default: return "SINK_DIAG";
+    }
+}
+}  // namespace
+
+// Names of the kernels (template instantiations) the job's passes launch for a sink, joined by
+// " + " -- what bench.py prints as roofline.kernel, so that the label follows the dispatch.
+extern "C" int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int g_dtype, char *buf,
+                           int64_t len)
+{
+    int st = validate(plan, job);
+    if (st != PF_OK) return st;
+    PF_CHECK_ARG(buf && len > 0, "null buffer");
+    PF_CHECK_ARG(sink >= SINK_STORE && sink <= SINK_DIAG, "bad sink");
+    static thread_local Pass passes[MAX_PASSES];
+    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
+    const char *gt = (sink == SINK_STORE && g_dtype == PF_F32) ? "float" : "double";
+    int64_t used = 0;
+    buf[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        const LaunchParams &p = passes[i].p;
+        char one[160];
+        int nr = 0;
+        if (sink == SINK_STORE || sink == SINK_FORWARD) nr = march_rounds(plan, p, sink == SINK_FORWARD);
+        if (nr)
+            snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,%s,%s,%d>", passes[i].family,
+                     prog_name(passes[i].prog), sink_name(sink), gt, nr);
+        else if (sink == SINK_GTV && plan->n_nodes > 0)
+            snprintf(one, sizeof(one), "pf_node_gtv_kernel<%d,%s>", passes[i].family, prog_name(passes[i].prog));
+        else
+            snprintf(one, sizeof(one), "pf_tile_kernel<%d,%s,%s,%s>", passes[i].family,
+                     prog_name(passes[i].prog), sink_name(sink), gt);
+        const int64_t need = (int64_t)strlen(one) + (i ? 3 : 0);
+        if (used + need + 1 > len) break;
+        if (i) { memcpy(buf + used, " + ", 3); used += 3; }
+        memcpy(buf + used, one, strlen(one));
+        used += (int64_t)strlen(one);
+        buf[used] = 0;
+    }
+    return PF_OK;
+}
+
 extern "C" int64_t pf_gt_dot_v_workspace_bytes(const pf_plan *plan, const pf_job *job)
 {
     if (!plan || !job) return -1;

@@ -231,6 +231,19 @@ class CudaEngine:
     def _jp(self, job):
         return ctypes.byref(self.plan), ctypes.byref(job)
 
+    def describe(self, sink="store"):
+        """Kernel instantiations the jobs of this engine launch for a sink ("store", "forward",
+        "gtv", "diag") -- asked from the library's own dispatch (``pf_describe``)."""
+        code = {"store": 0, "forward": 1, "gtv": 2, "diag": 3}[sink]
+        names = []
+        for job in self.jobs:
+            buf = ctypes.create_string_buffer(1024)
+            _lib.check(self.lib.pf_describe(*self._jp(job), code, self._g_code, buf, 1024), "pf_describe")
+            name = buf.value.decode()
+            if name and name not in names:
+                names.append(name)
+        return " ; ".join(names)
+
     # ----------------------------------------------------------- build / sinks
     def build_G(self):
         """Fill the local block of G on the device (rows_local x nP, row-major)."""

@@ -141,7 +141,11 @@ class ShardedDeviceOps:
         return self.rows_to_host(self.engine.gemv_dev(self.cols_to_device(x)))
 
     def gemv_t(self, y):
-        return self.cols_to_host(self.engine.gemv_t_dev(self.local_rows_of(y)))
+        return self.engine.to_host(self.gemv_t_allreduce_dev(self.local_rows_of(y)))
+
+    def gemv_t_allreduce_dev(self, y_local_t):
+        """z = sum over ranks of G_local^T y_local, on the device (the Jtvec of a sharded run)."""
+        return self.coll.all_reduce_sum(self.engine.gemv_t_dev(y_local_t))
 
     def G_to_numpy(self):
         if self.coll.world_size != 1:
