@@ -64,9 +64,14 @@ struct OutDesc {
     int blk;   // column block (0 for scalar models, 0..2 for vector models)
     int fi;    // index of the component inside this launch (forward partial sums)
     int last;  // last output of its component
-    int pad;
+    int role;  // ROLE_*: plain output, kept as operand A / B, or derived from A and B (no plane)
     double factor;  // gravity: G_newton * unit factor; magnetics: (1/4pi) * |B0|
 };
+// Derived outputs (marching kernel only).  gravity gzz needs no plane of its own: per node
+// kernel_ee + kernel_nn + kernel_uu = -(Aee + Ann + Auu) = -S with S = +-pi/2 or 0 (the atan
+// identity of eval_raw), so per cell  gzz = -(gxx + gyy) - factor * sum_vertices s_v S_v,  and
+// the last term vanishes unless the receiver lies inside or on the closed prism (cell_S below).
+enum { ROLE_PLAIN = 0, ROLE_KEEP_A = 1, ROLE_KEEP_B = 2, ROLE_DERIVED = 3 };
 
 struct LaunchParams {
     pf_plan plan;
@@ -84,6 +89,7 @@ struct LaunchParams {
     int raw_mask;      // raw kernels stored as planes: bit q set -> slot = rank of q among the set bits
     int n_combo;       // planes [n_planes - n_combo, n_planes) are DOT3 / QUAD combinations
     int n_buf;         // marching kernel: 2 = node planes double-buffered (one barrier per layer), 1 = single
+    int n_derived;     // outputs [n_out - n_derived, n_out) have no plane (ROLE_DERIVED)
     PlaneDesc planes[MAX_PLANES];
     OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
@@ -449,6 +455,19 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
 #define PF_MARCH_MIN_BLOCKS 3
 #endif
 
+// sign of a node's atan sum S = Aee + Ann + Auu as an integer: +-1 for +-pi/2, 0 when two or
+// more coordinates vanish (the safe_atan2 conventions, see eval_raw)
+__device__ __forceinline__ int node_S_sign(double e, double n, double u)
+{
+    const int zeros = (int)(e == 0.0) + (int)(n == 0.0) + (int)(u == 0.0);
+    const int sb = (__double2hiint(e) ^ __double2hiint(n) ^ __double2hiint(u)) & 0x80000000;
+    return zeros >= 2 ? 0 : (sb ? -1 : 1);
+}
+
+#ifndef PF_UNROLL_NODES
+#define PF_UNROLL_NODES 0
+#endif
+
 template <int FAM, int PROG, int SINK, typename GT, int NR>
 __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     pf_march_kernel(const __grid_constant__ LaunchParams p)
@@ -458,14 +477,17 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     extern __shared__ double smem[];
     const int n_planes = p.n_planes;
     const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
+    // outputs [0, n_plain) read a plane and own a dprev slot; [n_plain, n_out) are derived
+    const int n_plain = PF_IS_TMI(PROG) ? PROG : p.n_out - p.n_derived;
     const int buf_doubles = n_planes * NCAP;
     const int n_buf = p.n_buf;    // 1 when two buffers would not leave room for 3 CTAs per SM
-    double *dprev = smem + n_buf * (size_t)buf_doubles;       // [n_out][NR][THREADS] corner differences
-    double *wacc = dprev + (size_t)n_out * NR * PF_THREADS;   // [WARPS][n_fwd] (forward)
+    double *dprev = smem + n_buf * (size_t)buf_doubles;       // [n_plain][NR][THREADS] corner differences
+    double *wacc = dprev + (size_t)n_plain * NR * PF_THREADS; // [WARPS][n_fwd] (forward)
     // per-output bookkeeping, refreshed once per receiver: destination of column 0 of
-    // the output's row/block (store) or of its model block (forward), and its factor
+    // the output's row/block (store) or of its model block (forward), its factor and role
     __shared__ unsigned long long s_dst[MAX_OUT];
     __shared__ double s_fac[MAX_OUT];
+    __shared__ int s_role[MAX_OUT];
 
     const int tid = threadIdx.x;
     const int nx = p.plan.grid_nx, ny = p.plan.grid_ny;
@@ -474,13 +496,13 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const int iz_begin = fp[4], iz_end = fp[5];   // cell layers that hold active cells
     const int W1 = fw + 1;
     const int n_layer_nodes = W1 * (fh + 1);
-    const int n_layer_cells = fw * fh;
     const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
     const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
     const int64_t nC = p.plan.n_cells;
     const int64_t layer_stride = (int64_t)nx * ny;
     const int sW = W1 * 8;  // byte stride of one node row inside a layer plane
     const bool direct = PF_IS_TMI(PROG) || p.direct;
+    const bool has_derived = !PF_IS_TMI(PROG) && n_out > n_plain;
 
     // ---- footprint-stationary state -------------------------------------------
     double x[NR], y[NR];
@@ -492,6 +514,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
         x[k] = ok ? p.plan.grid_xs[ix0 + lx] : 0.0;
         y[k] = ok ? p.plan.grid_ys[iy0 + ly] : 0.0;
     }
+    const int n_layer_cells = fw * fh;
     int o00[NR];       // byte offset of the cell's (x0, y0) node inside a layer plane
     int cbase[NR];     // mesh index of the cell in layer 0, -1 = no cell in this slot
 #pragma unroll
@@ -505,6 +528,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     if (SINK == SINK_FORWARD) {
         for (int i = tid; i < WARPS * p.n_fwd; i += PF_THREADS) wacc[i] = 0.0;
     }
+    // closed (x, y) bounding box of the footprint's nodes (derived outputs only)
+    double box_x0 = 0, box_x1 = 0, box_y0 = 0, box_y1 = 0;
+    if (has_derived) {
+        box_x0 = __ldg(p.plan.grid_xs + ix0);
+        box_x1 = __ldg(p.plan.grid_xs + ix0 + fw);
+        box_y0 = __ldg(p.plan.grid_ys + iy0);
+        box_y1 = __ldg(p.plan.grid_ys + iy0 + fh);
+    }
 
     for (int64_t r = r_begin; r < r_end; ++r) {
         const double rx = __ldg(p.receivers + 3 * r);
@@ -517,17 +548,126 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                              ? (unsigned long long)(reinterpret_cast<GT *>(p.G) + row * p.ldG + (int64_t)od.blk * nC)
                              : (unsigned long long)(p.model + (int64_t)od.blk * nC);
             s_fac[tid] = od.factor;
+            s_role[tid] = od.role;
         }
+        // sum_v s_v S_v of a cell can only be non-zero when the receiver lies inside or on the
+        // closed prism: a CTA-uniform test per receiver (and per layer below) guards the exact path
+        const bool rx_in_box = has_derived && rx >= box_x0 && rx <= box_x1 && ry >= box_y0 && ry <= box_y1;
 
         // ---- phase 1: output planes of node layer L -> planes ---------------------------
         auto phase1 = [&](int L, double *planes) {
             const double u = __ldg(p.plan.grid_zs + L) - rz;
+#if PF_UNROLL_NODES
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                const int j = tid + k * PF_THREADS;
+                if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, x[k] - rx, y[k] - ry, u, planes, j);
+            }
+#else
 #pragma unroll 1
             for (int k = 0; k < NR; ++k) {
                 const int j = tid + k * PF_THREADS;
                 const double xx = (k == 0) ? x[0] : ((k == 1) ? x[1 % NR] : ((k == 2) ? x[2 % NR] : x[3 % NR]));
                 const double yy = (k == 0) ? y[0] : ((k == 1) ? y[1 % NR] : ((k == 2) ? y[2 % NR] : y[3 % NR]));
                 if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, planes, j);
+            }
+#endif
+        };
+        // exact sum_v s_v S_v of the cell in slot s between node layers L-1 and L (rare path)
+        auto cell_S = [&](int s, int L) -> double {
+            const int c = tid + s * PF_THREADS;
+            const int cy = c / fw, cx = c - cy * fw;
+            const double e0 = __ldg(p.plan.grid_xs + ix0 + cx) - rx, e1 = __ldg(p.plan.grid_xs + ix0 + cx + 1) - rx;
+            const double n0 = __ldg(p.plan.grid_ys + iy0 + cy) - ry, n1 = __ldg(p.plan.grid_ys + iy0 + cy + 1) - ry;
+            const double u0 = __ldg(p.plan.grid_zs + L - 1) - rz, u1 = __ldg(p.plan.grid_zs + L) - rz;
+            const int k = -node_S_sign(e0, n0, u0) + node_S_sign(e1, n0, u0) + node_S_sign(e0, n1, u0)
+                          - node_S_sign(e1, n1, u0) + node_S_sign(e0, n0, u1) - node_S_sign(e1, n0, u1)
+                          - node_S_sign(e0, n1, u1) + node_S_sign(e1, n1, u1);
+            return (double)k * 1.5707963267948966;
+        };
+        // ---- phase 2 for passes with derived outputs (gravity gzz from gxx and gyy): output-major,
+        //      plain outputs first (they fill keep_a / keep_b), then the derived ones -------------
+        auto phase2_derived = [&](int L, const double *planes) {
+            const char *pl = reinterpret_cast<const char *>(planes);
+            const bool emit = L > iz_begin;
+            int col[NR];
+            const int layer_off = (int)(layer_stride * (L - 1));
+            const int32_t *colmap = p.plan.grid_colmap;
+#pragma unroll
+            for (int s = 0; s < NR; ++s) {
+                col[s] = -1;
+                if (emit && cbase[s] >= 0) {
+                    const int idx = cbase[s] + layer_off;
+                    col[s] = colmap ? __ldg(colmap + idx) : idx;
+                }
+            }
+            // sum_v s_v S_v of a cell can only be non-zero when the receiver lies inside or on the
+            // closed prism: CTA-uniform guard (footprint box per receiver, z range per layer)
+            bool needS = false;
+            if (rx_in_box && emit) needS = rz >= __ldg(p.plan.grid_zs + L - 1) && rz <= __ldg(p.plan.grid_zs + L);
+            double keep_a[NR], keep_b[NR];
+#pragma unroll
+            for (int s = 0; s < NR; ++s) keep_a[s] = keep_b[s] = 0.0;
+            double fsum = 0.0;
+#define PF_PHASE2_PLAIN(O, POFF)                                                                  \
+            {                                                                                     \
+                GT *grow = reinterpret_cast<GT *>(s_dst[O]);                                      \
+                const double *mrow = reinterpret_cast<const double *>(s_dst[O]);                  \
+                const double factor = s_fac[O];                                                   \
+                const int role = s_role[O];                                                       \
+                double *dp = dprev + (size_t)(O) * (NR * PF_THREADS) + tid;                       \
+                _Pragma("unroll") for (int s = 0; s < NR; ++s) {                                  \
+                    if (cbase[s] < 0) continue;                                                   \
+                    const char *q = pl + (POFF) + o00[s];                                         \
+                    const double d_new = *reinterpret_cast<const double *>(q)                     \
+                                         - *reinterpret_cast<const double *>(q + 8)               \
+                                         - *reinterpret_cast<const double *>(q + sW)              \
+                                         + *reinterpret_cast<const double *>(q + sW + 8);         \
+                    const double d_old = dp[s * PF_THREADS];                                      \
+                    dp[s * PF_THREADS] = d_new;                                                   \
+                    const double g = factor * (d_new - d_old);                                    \
+                    if (role == ROLE_KEEP_A) keep_a[s] = g;                                       \
+                    if (role == ROLE_KEEP_B) keep_b[s] = g;                                       \
+                    if (col[s] < 0) continue;                                                     \
+                    if (SINK == SINK_STORE) grow[(unsigned)col[s]] = (GT)g;                       \
+                    else fsum += g * __ldg(mrow + (unsigned)col[s]);                              \
+                }                                                                                 \
+                if (SINK == SINK_FORWARD && emit && p.outs[O].last) {                             \
+                    fsum = warp_sum(fsum);                                                        \
+                    if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd + p.outs[O].fi] += fsum;       \
+                    fsum = 0.0;                                                                   \
+                }                                                                                 \
+            }
+            if (direct) {
+#pragma unroll
+                for (int o = 0; o < MAX_PLANES; ++o) {
+                    if (o >= n_plain) break;
+                    PF_PHASE2_PLAIN(o, o * LAYER_BYTES)
+                }
+            } else {
+                for (int o = 0; o < n_plain; ++o) {
+                    const int poff = p.outs[o].plane * LAYER_BYTES;
+                    PF_PHASE2_PLAIN(o, poff)
+                }
+            }
+#undef PF_PHASE2_PLAIN
+            for (int o = n_plain; o < n_out; ++o) {
+                GT *grow = reinterpret_cast<GT *>(s_dst[o]);
+                const double *mrow = reinterpret_cast<const double *>(s_dst[o]);
+                const double factor = s_fac[o];
+#pragma unroll
+                for (int s = 0; s < NR; ++s) {
+                    if (col[s] < 0) continue;
+                    double g = -(keep_a[s] + keep_b[s]);
+                    if (needS) g -= factor * cell_S(s, L);
+                    if (SINK == SINK_STORE) grow[(unsigned)col[s]] = (GT)g;
+                    else fsum += g * __ldg(mrow + (unsigned)col[s]);
+                }
+                if (SINK == SINK_FORWARD && emit) {
+                    fsum = warp_sum(fsum);
+                    if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd + p.outs[o].fi] += fsum;
+                    fsum = 0.0;
+                }
             }
         };
         // ---- phase 2: corner differences of layer L; emits the cells between L-1 and L ----
@@ -636,9 +776,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
         // node layers iz_begin .. iz_end; the cells between layers L-1 and L are emitted at L
         for (int L = iz_begin; L <= iz_end; ++L) {
             double *planes = smem + ((n_buf == 2) ? (L & 1) * buf_doubles : 0);
+#ifndef PF_ABLATE_P1      // timing experiments only (results are garbage)
             phase1(L, planes);
+#endif
             __syncthreads();
-            phase2(L, planes);
+#ifndef PF_ABLATE_P2
+            if (has_derived) phase2_derived(L, planes);
+            else phase2(L, planes);
+#endif
             if (n_buf == 1) __syncthreads();
         }
         __syncthreads();   // all warps done with the last layer (buffers, dprev and wacc are reused)
@@ -953,7 +1098,7 @@ bool add_component(const pf_job *job, int c, const CompInfo &ci, double amp, Lau
         od.blk = b;
         od.fi = p.n_fwd;
         od.last = (b == nblk - 1);
-        od.pad = 0;
+        od.role = ROLE_PLAIN;
         od.factor = factor;
     }
     p.n_fwd++;
@@ -980,9 +1125,20 @@ void init_pass(const pf_plan *plan, const pf_job *job, double amp, Pass &pass, i
     }
 }
 
-// Split the job into passes (usually one per kernel family).
-int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_passes)
+// Split the job into passes (usually one per kernel family).  allow_derived: gravity gzz is
+// produced from the gxx and gyy outputs of the same pass instead of a plane of its own (ROLE_*;
+// only the marching kernel understands derived outputs).
+int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_passes, bool allow_derived = false)
 {
+    int c_gxx = -1, c_gyy = -1, c_gzz = -1;
+    if (allow_derived && job->physics == PF_GRAVITY) {
+        for (int c = 0; c < job->n_components; ++c) {
+            if (job->components[c] == PF_GXX && c_gxx < 0) c_gxx = c;
+            if (job->components[c] == PF_GYY && c_gyy < 0) c_gyy = c;
+            if (job->components[c] == PF_GZZ && c_gzz < 0) c_gzz = c;
+        }
+    }
+    const bool derive_gzz = c_gxx >= 0 && c_gyy >= 0 && c_gzz >= 0;
     double amp = 1.0;
     if (job->physics == PF_MAGNETICS) {
         const double fx = job->b0[0], fy = job->b0[1], fz = job->b0[2];
@@ -996,6 +1152,7 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
             CompInfo ci;
             component_info(job->physics, job->components[c], ci);
             if (ci.family != family) continue;
+            if (derive_gzz && job->components[c] == PF_GZZ) continue;   // appended below, no plane
             if (!open) {
                 if (n == max_passes) return -1;
                 init_pass(plan, job, amp, passes[n], family);
@@ -1065,6 +1222,32 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
         p.direct = 1;
         for (int o = 0; o < p.n_out; ++o)
             if (p.outs[o].plane != o) p.direct = 0;
+        p.n_derived = 0;
+        if (derive_gzz && passes[i].family == 12) {
+            // the pass that holds gxx also holds gyy (gravity never needs more than one family-12
+            // pass: at most 9 planes); every gzz row of the job is derived from them
+            int oa = -1, ob = -1;
+            for (int o = 0; o < p.n_out; ++o) {
+                if (p.outs[o].ci == c_gxx) oa = o;
+                if (p.outs[o].ci == c_gyy) ob = o;
+            }
+            if (oa < 0 || ob < 0) return -1;
+            p.outs[oa].role = ROLE_KEEP_A;
+            p.outs[ob].role = ROLE_KEEP_B;
+            for (int c = 0; c < job->n_components; ++c) {
+                if (job->components[c] != PF_GZZ) continue;
+                if (p.n_out == MAX_OUT || p.n_fwd == PF_MAX_COMPONENTS) return -1;
+                OutDesc &od = p.outs[p.n_out++];
+                od.plane = 0;
+                od.ci = c;
+                od.blk = 0;
+                od.fi = p.n_fwd++;
+                od.last = 1;
+                od.role = ROLE_DERIVED;
+                od.factor = p.outs[oa].factor;
+                p.n_derived++;
+            }
+        }
         passes[i].prog = PROG_GENERIC;
         if (passes[i].family == 12 && job->physics == PF_MAGNETICS && p.n_fwd == 1 &&
             job->components[p.outs[0].ci] == PF_TMI)
@@ -1132,8 +1315,8 @@ constexpr size_t MARCH_SMEM_LIMIT = 110 * 1024;  // keeps >= 2 CTAs per SM
 
 size_t march_smem_n(const LaunchParams &p, int nr, bool forward, int n_buf)
 {
-    return (((size_t)n_buf * p.n_planes + p.n_out) * nr * PF_THREADS + (forward ? WARPS * p.n_fwd : 0))
-           * sizeof(double);
+    return (((size_t)n_buf * p.n_planes + (p.n_out - p.n_derived)) * nr * PF_THREADS
+            + (forward ? WARPS * p.n_fwd : 0)) * sizeof(double);
 }
 
 // double-buffered node planes (one barrier per layer) unless that costs the third CTA per SM and
@@ -1200,6 +1383,21 @@ int launch_march(const Pass &pass, int nr, cudaStream_t stream)
     return (nr == 4) ? launch_march_nr<SINK, GT, 4>(pass, stream) : launch_march_nr<SINK, GT, 2>(pass, stream);
 }
 
+// Passes of the sinks that can run on the marching kernel (store, forward): derived outputs are
+// used when every pass of the job then runs on it, otherwise the plain schedule.
+int make_passes_march(const pf_plan *plan, const pf_job *job, Pass *passes, bool forward)
+{
+    if (plan->grid_nx > 0) {
+        const int n = make_passes(plan, job, passes, MAX_PASSES, true);
+        bool derived = false, ok = n >= 0;
+        for (int i = 0; ok && i < n; ++i) derived = derived || passes[i].p.n_derived > 0;
+        if (ok && !derived) return n;
+        for (int i = 0; ok && i < n; ++i) ok = march_rounds(plan, passes[i].p, forward) != 0;
+        if (ok) return n;
+    }
+    return make_passes(plan, job, passes, MAX_PASSES, false);
+}
+
 int validate_grid(const pf_plan *plan)
 {
     if (plan->grid_nx == 0) return PF_OK;
@@ -1231,7 +1429,7 @@ extern "C" int pf_job_uses_marching(const pf_plan *plan, const pf_job *job, int 
     if (validate(plan, job) != PF_OK) return 0;
     if (plan->grid_nx <= 0) return 0;
     static thread_local Pass passes[MAX_PASSES];
-    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    const int n = make_passes_march(plan, job, passes, forward != 0);
     if (n <= 0) return 0;
     for (int i = 0; i < n; ++i)
         if (!march_rounds(plan, passes[i].p, forward != 0)) return 0;
@@ -1250,7 +1448,7 @@ extern "C" int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64
     st = validate_grid(plan);
     if (st != PF_OK) return st;
     static thread_local Pass passes[MAX_PASSES];
-    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    const int n = make_passes_march(plan, job, passes, false);
     PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
     for (int i = 0; i < n; ++i) {
         LaunchParams &p = passes[i].p;
@@ -1338,7 +1536,7 @@ static int pf_forward_chunk(const pf_plan *plan, const pf_job *job, const double
 {
     int st = PF_OK;
     static thread_local Pass passes[MAX_PASSES];
-    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    const int n = make_passes_march(plan, job, passes, true);
     PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
     for (int i = 0; i < n; ++i) {
         LaunchParams &p = passes[i].p;
@@ -1495,7 +1693,9 @@ extern "C" int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int
     PF_CHECK_ARG(buf && len > 0, "null buffer");
     PF_CHECK_ARG(sink >= SINK_STORE && sink <= SINK_DIAG, "bad sink");
     static thread_local Pass passes[MAX_PASSES];
-    const int n = make_passes(plan, job, passes, MAX_PASSES);
+    const int n = (sink == SINK_STORE || sink == SINK_FORWARD)
+                      ? make_passes_march(plan, job, passes, sink == SINK_FORWARD)
+                      : make_passes(plan, job, passes, MAX_PASSES);
     PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
     const char *gt = (sink == SINK_STORE && g_dtype == PF_F32) ? "float" : "double";
     int64_t used = 0;

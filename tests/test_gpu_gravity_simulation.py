@@ -49,8 +49,11 @@ def test_G_matches_oracle(components):
 @pytest.mark.parametrize("store", ["ram", "forward_only"])
 @pytest.mark.parametrize("transpose", [False, True], ids=["J @ m", "J.T @ v"])
 def test_getJ_as_linear_operator(mapping, store, transpose):
-    # test_forward_Grav_Linear.py:476-524 (engine="cuda" always returns an operator)
+    # test_forward_Grav_Linear.py:499-524: an operator for 'forward_only' (and for 'ram' once the
+    # matrix is too large for the host: getJ_dense_max_bytes)
     sim, mesh, rho, model = make_sim("gz", store, mapping)
+    if store == "ram":
+        sim.getJ_dense_max_bytes = 0
     jac = sim.getJ(model)
     assert isinstance(jac, LinearOperator)
     G = oracle_for(sim).sensitivity_matrix()
@@ -60,6 +63,20 @@ def test_getJ_as_linear_operator(mapping, store, transpose):
         np.testing.assert_allclose(jac.T @ vector, deriv.T @ (G.T @ vector), rtol=1e-9)
     else:
         np.testing.assert_allclose(jac @ model, G @ (deriv.diagonal() * model), rtol=1e-9)
+
+
+@pytest.mark.parametrize("mapping", ["identity_map", "exp_map"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_getJ_as_array(mapping, dtype):
+    # test_forward_Grav_Linear.py:476-497: a dense ndarray for store_sensitivities="ram";
+    # with an identity mapping it is G itself, otherwise G @ mapping.deriv(model)
+    sim, mesh, rho, model = make_sim("gz", "ram", mapping, dtype=dtype)
+    jac = sim.getJ(model)
+    assert isinstance(jac, np.ndarray) and jac.shape == (sim.survey.nD, mesh.n_cells)
+    G = oracle_for(sim).sensitivity_matrix()
+    expected = G if mapping == "identity_map" else G @ sim.rhoMap.deriv(model)
+    tol = RTOL_NORMWISE if dtype is np.float64 else 1e-6
+    assert rowwise_rel(np.asarray(jac, dtype=np.float64), np.asarray(expected)).max() <= tol
 
 
 @pytest.mark.parametrize("mapping", ["identity_map", "exp_map"])
