@@ -293,6 +293,11 @@ int pf_cg_update(const double *p, const double *q, const double *minv, int64_t n
                  void *stream);
 int pf_cg_direction(const double *h, int64_t n, double *p, double *scal, void *stream);
 int pf_vec_mul(const double *a, const double *b, int64_t n, double *out, void *stream);
+/* y = A x, A in CSR (int32 indptr [n_rows + 1] / indices, fp64 values): the sparse model-map derivative
+ * (maps.TileMap, maps.Wires, any LinearMap; gravity/simulation.py:386-387, 418-419 apply it on the host)
+ * and its transpose around pf_gemv / pf_gemv_t inside the device CG loop. */
+int pf_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *values, int64_t n_rows,
+                const double *x, double *y, void *stream);
 
 /*
  * Host-side generic tile planner (HOST pointers; no CUDA calls): recursive coordinate bisection of

@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = (
     "pf_plan_tensor_count", "pf_plan_tensor_fill",
     "pf_probe_fp64_peak",
     "pf_cg_workspace_bytes", "pf_cg_init", "pf_cg_hvp_combine", "pf_cg_update", "pf_cg_direction",
-    "pf_vec_mul", "pf_host_copy", "pf_math_probe",
+    "pf_vec_mul", "pf_csr_spmv", "pf_host_copy", "pf_math_probe",
     "pf_plan_generic_assign", "pf_plan_generic_fill",
 )
 
@@ -135,6 +135,7 @@ def load_library() -> ctypes.CDLL:
         "pf_cg_update": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
         "pf_cg_direction": (i32, [vp, i64, vp, vp, vp]),
         "pf_vec_mul": (i32, [vp, vp, i64, vp, vp]),
+        "pf_csr_spmv": (i32, [vp, vp, vp, i64, vp, vp, vp]),
         "pf_host_copy": (i32, [vp, vp, i64]),
         "pf_math_probe": (i32, [i32, vp, vp, vp, vp, i64, vp]),
         "pf_plan_generic_assign": (i64, [vp, i64, vp, i64, vp]),

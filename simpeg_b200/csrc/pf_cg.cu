@@ -20,13 +20,15 @@
 namespace {
 
 constexpr int CG_THREADS = 256;
-constexpr int CG_MAX_BLOCKS = 1184;   // 148 SMs x 8 CTAs
+constexpr int CG_MAX_BLOCKS = 2048;   // workspace bound; launches use 8 CTAs per SM of the device
 enum { S_SOLD = 0, S_PQ = 1, S_RR = 2, S_SNEW = 3 };
 
 int cg_blocks(int64_t n)
 {
     int64_t b = pf_ceil_div(n > 0 ? n : 1, CG_THREADS);
-    return (int)(b < CG_MAX_BLOCKS ? b : CG_MAX_BLOCKS);
+    int64_t cap = (int64_t)pf_sm_count() * 8;
+    if (cap > CG_MAX_BLOCKS) cap = CG_MAX_BLOCKS;
+    return (int)(b < cap ? b : cap);
 }
 
 // block sum of two quantities; thread 0 writes partial[blockIdx.x] and partial[gridDim.x + blockIdx.x]
@@ -164,6 +166,21 @@ __global__ void __launch_bounds__(CG_THREADS) vec_mul_kernel(const double *__res
         out[i] = a[i] * b[i];
 }
 
+// y = A x for a CSR matrix (one thread per row): the model-map derivative of a TileMap / Wires /
+// LinearMap mapping and its transpose around the two products over G
+__global__ void __launch_bounds__(CG_THREADS) csr_spmv_kernel(const int32_t *__restrict__ indptr,
+                                                              const int32_t *__restrict__ indices,
+                                                              const double *__restrict__ values, int64_t n_rows,
+                                                              const double *__restrict__ x, double *__restrict__ y)
+{
+    for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * CG_THREADS) {
+        double t = 0.0;
+        const int32_t k1 = indptr[i + 1];
+        for (int32_t k = indptr[i]; k < k1; ++k) t = fma(values[k], __ldg(x + indices[k]), t);
+        y[i] = t;
+    }
+}
+
 int check_ws(const void *ws, int64_t bytes, int64_t n)
 {
     if (!ws || bytes < pf_cg_workspace_bytes(n)) {
@@ -262,6 +279,19 @@ extern "C" int pf_vec_mul(const double *a, const double *b, int64_t n, double *o
     if (n == 0) return PF_OK;
     PF_CHECK_ARG(a && b && out, "null vector");
     vec_mul_kernel<<<cg_blocks(n), CG_THREADS, 0, stream>>>(a, b, n, out);
+    PF_COUNT_LAUNCH();
+    PF_CUDA_OK(cudaGetLastError());
+    return PF_OK;
+}
+
+extern "C" int pf_csr_spmv(const int32_t *indptr, const int32_t *indices, const double *values, int64_t n_rows,
+                           const double *x, double *y, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PF_CHECK_ARG(n_rows >= 0, "negative row count");
+    if (n_rows == 0) return PF_OK;
+    PF_CHECK_ARG(indptr && y, "null pointer");
+    csr_spmv_kernel<<<cg_blocks(n_rows), CG_THREADS, 0, stream>>>(indptr, indices, values, n_rows, x, y);
     PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;

@@ -36,8 +36,8 @@ class DeviceGaussNewtonCG:
     Parameters
     ----------
     simulation : gravity / magnetics ``Simulation3DIntegral`` (or equivalent-source layer) with
-        ``engine="cuda"``, ``store_sensitivities="ram"``; its model map must have a diagonal
-        derivative (identity, exp, ...).
+        ``engine="cuda"``, ``store_sensitivities="ram"``; the derivative of its model map may be
+        the identity, diagonal (exp, ...) or any sparse matrix (``TileMap``, ``Wires``, ``LinearMap``).
     data_weights : (nD,) array, optional
         Diagonal of ``W`` of the data misfit (1 / standard deviation); default ones.
     reg_hessian : None | (nP,) array | scipy.sparse matrix (nP, nP)
@@ -126,20 +126,34 @@ class DeviceGaussNewtonCG:
             self._reg_diag_host = d
 
     def set_model(self, m):
-        """Linearisation point: fixes the (diagonal) derivative of the model map."""
+        """Linearisation point: fixes the derivative of the model map -- the identity, a diagonal
+        (``ExpMap`` ...) or a general sparse matrix (``maps.TileMap``, ``maps.Wires``,
+        ``LinearMap``: applied as device CSR products around the two products over G)."""
         sim = self.simulation
         sim.model = m
         deriv = sim.rhoDeriv if sim._physics == "gravity" else sim.chiDeriv
         n = int(np.asarray(m).size)
-        if getattr(deriv, "is_identity", False):
-            self._deriv_t, self._deriv_host = None, None
-        else:
+        torch, dev = self.torch, self.engine.device
+        self._deriv_t = self._deriv_host = self._csr = self._csr_t = None
+        if not getattr(deriv, "is_identity", False):
             D = sp.csr_matrix(deriv)
-            if D.shape != (self.nP, n) or self.nP != n or (D - sp.diags(D.diagonal())).nnz != 0:
-                raise NotImplementedError(
-                    "the device CG loop needs a model map with a diagonal derivative")
-            self._deriv_host = np.asarray(D.diagonal(), dtype=np.float64)
-            self._deriv_t = self.torch.from_numpy(self._deriv_host).to(self.engine.device)
+            if D.shape != (self.nP, n):
+                raise ValueError(f"the model-map derivative must be ({self.nP}, {n}), got {D.shape}")
+            if self.nP == n and (D - sp.diags(D.diagonal())).nnz == 0:
+                self._deriv_host = np.asarray(D.diagonal(), dtype=np.float64)
+                self._deriv_t = torch.from_numpy(self._deriv_host).to(dev)
+            else:
+                if D.nnz >= 2**31:
+                    raise ValueError("model-map derivative has too many non-zeros for int32 indices")
+
+                def upload(A):
+                    A = sp.csr_matrix(A)
+                    A.sort_indices()
+                    return (torch.from_numpy(A.indptr.astype(np.int32)).to(dev),
+                            torch.from_numpy(A.indices.astype(np.int32)).to(dev),
+                            torch.from_numpy(A.data.astype(np.float64)).to(dev))
+
+                self._csr, self._csr_t = upload(D), upload(D.T)
         if self.n_model != n:
             self.n_model = n
             self._upload_reg(n)
@@ -160,8 +174,15 @@ class DeviceGaussNewtonCG:
         return out
 
     # ----------------------------------------------------------------- products
+    def _spmv(self, csr, n_rows, x_t):
+        y = self.torch.empty(n_rows, dtype=self.torch.float64, device=self.engine.device)
+        _lib.check(self.lib.pf_csr_spmv(csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr(), n_rows,
+                                        x_t.data_ptr(), y.data_ptr(), self.engine._stream()), "pf_csr_spmv")
+        return y
+
     def _normal_product(self, p_t):
-        """z = G^T W^2 G (d * p) summed over ranks (device tensors)."""
+        """z = D^T G^T W^2 G D p summed over ranks (device tensors; D = model-map derivative:
+        identity, diagonal -- its transpose is applied inside pf_cg_hvp_combine -- or CSR)."""
         eng, lib = self.engine, self.lib
         stream = eng._stream()
         torch = self.torch
@@ -170,25 +191,35 @@ class DeviceGaussNewtonCG:
             x = torch.empty_like(p_t)
             _lib.check(lib.pf_vec_mul(self._deriv_t.data_ptr(), p_t.data_ptr(), self.nP, x.data_ptr(),
                                       stream), "pf_vec_mul")
+        elif self._csr is not None:
+            x = self._spmv(self._csr, self.nP, p_t)
         y = eng.gemv_dev(x)
         _lib.check(lib.pf_vec_mul(y.data_ptr(), self._w2_local.data_ptr(), y.numel(), y.data_ptr(),
                                   stream), "pf_vec_mul")
-        z = eng.gemv_t_dev(y)
-        return self.ops.coll.all_reduce_sum(z)
+        z = self.ops.gemv_t_allreduce_dev(y)        # column slabs overlapped with their all-reduce
+        if self._csr_t is not None:
+            z = self._spmv(self._csr_t, self.n_model, z)
+        return z
 
     def _hvp_combine(self, z, p, q, mask):
         eng = self.engine
         _lib.check(self.lib.pf_cg_hvp_combine(
             z.data_ptr(), self._ptr(self._deriv_t), p.data_ptr(), self._ptr(self._indptr),
             self._ptr(self._indices), self._ptr(self._values), self._ptr(self._rdiag),
-            ctypes.c_double(2.0), ctypes.c_double(self.beta), self._ptr(mask), self.nP, q.data_ptr(),
+            ctypes.c_double(2.0), ctypes.c_double(self.beta), self._ptr(mask), self.n_model, q.data_ptr(),
             self._scal.data_ptr(), self._ws.data_ptr(), self._ws.numel() * 8, eng._stream()),
             "pf_cg_hvp_combine")
+
+    def _model_to_device(self, v):
+        """(n_model,) host vector -> device (rank-sliced upload when it has nP entries)."""
+        if self.n_model == self.nP:
+            return self.ops.cols_to_device(v)
+        return self.engine.to_device(v, n=self.n_model)
 
     def hessian_vector(self, v):
         """``H v = 2 J^T W^T W J v + beta R v`` for a host vector (device round trip; tests)."""
         eng = self.engine
-        p = self.ops.cols_to_device(v)
+        p = self._model_to_device(v)
         q = self.torch.empty_like(p)
         with self.torch.cuda.device(eng.device):
             self._hvp_combine(self._normal_product(p), p, q, None)
@@ -218,18 +249,26 @@ class DeviceGaussNewtonCG:
         eng, lib, torch = self.engine, self.lib, self.torch
         g = np.ascontiguousarray(g, dtype=np.float64).reshape(-1)
         xc = self._m if xc is None else np.asarray(xc, dtype=np.float64).reshape(-1)
-        n = self.nP
+        n = self.n_model
         if g.shape != (n,) or xc.shape != (n,):
             raise ValueError(f"gradient and model must have {n} entries")
-        active, bound = self._bounds_sets(xc, g)
-        inactive = ~active
+        # no finite bound: every variable is free (activeSet / bindingSet of optimization.py:981-1018
+        # are empty) -- skip the six passes over (nP,) host vectors they cost
+        unbounded = (self.lower is None or np.all(np.isneginf(self.lower))) and \
+            (self.upper is None or np.all(np.isposinf(self.upper)))
+        if unbounded:
+            active = bound = inactive = None
+        else:
+            active, bound = self._bounds_sets(xc, g)
+            inactive = ~active
         ws, wsb = self._ws.data_ptr(), self._ws.numel() * 8
         with torch.cuda.device(eng.device):
             stream = eng._stream()
-            g_t = self.ops.cols_to_device(g)
-            mask = None if inactive.all() else torch.from_numpy(inactive.astype(np.uint8)).to(eng.device)
+            g_t = self._model_to_device(g)
+            mask = None if (unbounded or inactive.all()) else \
+                torch.from_numpy(inactive.astype(np.uint8)).to(eng.device)
             if self._approx_hinv is not None and self._minv_t is None:
-                self._minv_t = self.ops.cols_to_device(self._approx_hinv)
+                self._minv_t = self._model_to_device(self._approx_hinv)
             minv = self._minv_t
             step, r, p, q, h = (torch.empty(n, dtype=torch.float64, device=eng.device) for _ in range(5))
             scal = self._scal
@@ -254,6 +293,8 @@ class DeviceGaussNewtonCG:
         self.cg_rel_resid = r_norm / r_norm0 if r_norm0 else 0.0
 
         # optimization.py:1688-1709: gradient on the active, non-binding set; zero the binding set
+        if unbounded:
+            return step_host
         active_not_bound = active & (~bound)
         if self.step_active_set and np.any(active_not_bound):
             rhs_a = active_not_bound * -g

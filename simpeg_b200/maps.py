@@ -61,3 +61,24 @@ class ExpMap(IdentityMap):
     def deriv(self, m, v=None):
         d = sp.diags(np.exp(np.asarray(m, dtype=np.float64)), format="csr")
         return d if v is None else d @ v
+
+
+class LinearMap(IdentityMap):
+    """``m -> A m`` for a (sparse) matrix ``A`` (simpeg.maps.LinearMap): the stand-in for the
+    mappings of tiled workflows -- ``maps.TileMap`` (global octree -> local mesh, a sparse
+    volume-averaging matrix) and ``maps.Wires`` / ``InjectActiveCells`` (selections) all act on
+    this path as a fixed sparse matrix with ``deriv(m) = A``."""
+
+    def __init__(self, A):
+        self.A = sp.csr_matrix(A)
+        self.nP = self.A.shape[1]
+
+    @property
+    def shape(self):
+        return self.A.shape
+
+    def _transform(self, m):
+        return np.asarray(self.A @ np.asarray(m, dtype=np.float64))
+
+    def deriv(self, m, v=None):
+        return self.A if v is None else self.A @ v

@@ -30,6 +30,26 @@ ENGINES = ("geoana", "choclo", "cuda")
 SLICED_UPLOAD_MIN = 1 << 18   # replicated host vectors at least this long are uploaded in rank slices
 
 
+JTVEC_SLABS = int(os.environ.get("PF_JTVEC_SLABS", "2"))               # column slabs of a sharded Jtvec (kernel of slab k+1 overlaps all-reduce of k)
+JTVEC_SLAB_ALIGN = 4096       # slab starts are multiples of this many columns (aligned 128-bit loads)
+JTVEC_SLAB_MIN = 1 << 18      # narrower matrices are not split
+
+
+def column_slabs(n, n_slabs, align=None, min_width=None):
+    """[0, n) cut into at most ``n_slabs`` ranges whose starts are multiples of ``align`` columns
+    and which are at least ``min_width`` wide (narrow matrices are not worth splitting)."""
+    align = JTVEC_SLAB_ALIGN if align is None else align
+    min_width = JTVEC_SLAB_MIN if min_width is None else min_width
+    k = max(1, min(int(n_slabs), n // min_width))
+    bounds = [0]
+    for j in range(1, k):
+        b = (n * j // k) // align * align
+        if b > bounds[-1]:
+            bounds.append(b)
+    bounds.append(n)
+    return [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i]]
+
+
 class _Zero:
     """Stand-in for ``simpeg.utils.Zero`` (derivative of a fixed property)."""
 
@@ -143,9 +163,25 @@ class ShardedDeviceOps:
     def gemv_t(self, y):
         return self.engine.to_host(self.gemv_t_allreduce_dev(self.local_rows_of(y)))
 
-    def gemv_t_allreduce_dev(self, y_local_t):
-        """z = sum over ranks of G_local^T y_local, on the device (the Jtvec of a sharded run)."""
-        return self.coll.all_reduce_sum(self.engine.gemv_t_dev(y_local_t))
+    def gemv_t_allreduce_dev(self, y_local_t, out=None):
+        """z = sum over ranks of G_local^T y_local, on the device (the Jtvec of a sharded run).
+
+        The column-owner kernel works on disjoint column slabs, so the all-reduce of a finished
+        slab runs (NCCL, its own stream) while the next slab is still streaming G: only the last
+        slab's reduction is exposed instead of the whole (nP,) vector (24 MB at BASELINE config 4).
+        """
+        eng, coll = self.engine, self.coll
+        if coll.world_size == 1:
+            return eng.gemv_t_dev(y_local_t, out=out)
+        n = eng.nP
+        z = eng.torch.empty(n, dtype=eng.torch.float64, device=eng.device) if out is None else out
+        works = []
+        for c0, c1 in column_slabs(n, JTVEC_SLABS):
+            eng.gemv_t_dev(y_local_t, out=z, cols=(c0, c1))
+            works.append(coll.all_reduce_sum_async(z[c0:c1]))
+        for w in works:
+            w.wait()                      # the compute stream waits for the reductions, not the host
+        return z
 
     def G_to_numpy(self):
         if self.coll.world_size != 1:

@@ -105,6 +105,13 @@ class ReceiverSharding:
         return cache[key]
 
 
+class _Done:
+    """Completed-work handle of a single-process "collective"."""
+
+    def wait(self):
+        return True
+
+
 class Collectives:
     """Thin wrapper over ``torch.distributed`` (a no-op for a single process)."""
 
@@ -139,6 +146,14 @@ class Collectives:
         if self._dist is not None:
             self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
         return tensor
+
+    def all_reduce_sum_async(self, tensor):
+        """Start the in-place sum over ranks and return a handle whose ``wait()`` orders the
+        current stream after it (NCCL runs the reduction on its own stream, so kernels launched
+        in between overlap with it)."""
+        if self._dist is None:
+            return _Done()
+        return self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def all_gather_slices(self, make_slice, n):
         """Full (n,) device vector from equal slices: rank r provides ``make_slice(lo, hi)`` for its

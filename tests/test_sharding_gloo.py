@@ -47,7 +47,27 @@ def _worker(rank, world, port, name, out_dir):
         assert np.array_equal(full.numpy(), model)
         odd = np.arange(7.0)
         assert np.array_equal(coll.all_gather_slices(lambda lo, hi: torch.from_numpy(odd[lo:hi].copy()), 7).numpy(), odd)
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), fwd=fwd, gtv=gtv)
+        # the slab-overlapped Jtvec (ShardedDeviceOps.gemv_t_allreduce_dev): column slabs, one async
+        # all-reduce per slab, waits at the end -- with a numpy stand-in for the device kernel
+        from simpeg_b200.potential_fields import base
+
+        base.JTVEC_SLABS, base.JTVEC_SLAB_ALIGN, base.JTVEC_SLAB_MIN = 3, 4, 8
+        G_t = torch.from_numpy(G_local)
+
+        class Engine:
+            nP, device = G_local.shape[1], torch.device("cpu")
+
+            def gemv_t_dev(self, y, out=None, cols=None):
+                c0, c1 = (0, self.nP) if cols is None else cols
+                z = torch.empty(self.nP, dtype=torch.float64) if out is None else out
+                z[c0:c1] = G_t[:, c0:c1].T @ y
+                return z
+
+        Engine.torch = torch
+        ops = base.ShardedDeviceOps(Engine(), coll, sh)
+        assert len(base.column_slabs(Engine.nP, base.JTVEC_SLABS)) == 3
+        gtv_slabs = ops.gemv_t_allreduce_dev(torch.from_numpy(case["v"][sh.local_rows])).numpy()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), fwd=fwd, gtv=gtv, gtv_slabs=gtv_slabs)
     finally:
         dist.destroy_process_group()
 
@@ -61,3 +81,4 @@ def test_two_rank_sharding(name, tmp_path):
         z = np.load(tmp_path / f"r{rank}.npz")
         assert np.array_equal(z["fwd"], case["fwd"])                      # all-gather is exact
         assert np.max(np.abs(z["gtv"] - case["gtv"])) <= 1e-13 * np.max(np.abs(case["gtv"]))
+        assert np.max(np.abs(z["gtv_slabs"] - case["gtv"])) <= 1e-13 * np.max(np.abs(case["gtv"]))
