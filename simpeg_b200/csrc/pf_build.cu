@@ -1321,7 +1321,10 @@ size_t march_smem_n(const LaunchParams &p, int nr, bool forward, int n_buf)
 
 // double-buffered node planes (one barrier per layer) unless that costs the third CTA per SM and
 // a single buffer (two barriers per layer) keeps it
-constexpr size_t MARCH_SMEM_3CTAS = 74 * 1024;
+#ifndef PF_MARCH_SMEM_BUDGET
+#define PF_MARCH_SMEM_BUDGET (74 * 1024)
+#endif
+constexpr size_t MARCH_SMEM_3CTAS = PF_MARCH_SMEM_BUDGET;
 int march_buffers(const LaunchParams &p, int nr, bool forward)
 {
     if (march_smem_n(p, nr, forward, 2) > MARCH_SMEM_3CTAS && march_smem_n(p, nr, forward, 1) <= MARCH_SMEM_3CTAS)
@@ -1339,7 +1342,9 @@ size_t march_smem(const LaunchParams &p, int nr, bool forward)
 int march_rounds(const pf_plan *plan, const LaunchParams &p, bool forward)
 {
     if (plan->grid_nx <= 0) return 0;
+#ifndef PF_PREFER_NR2
     if (plan->n_footprints4 > 0 && p.n_planes <= 3 && march_smem(p, 4, forward) <= MARCH_SMEM_LIMIT) return 4;
+#endif
     if (plan->n_footprints2 > 0 && march_smem(p, 2, forward) <= MARCH_SMEM_LIMIT) return 2;
     return 0;
 }
