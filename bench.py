@@ -485,9 +485,15 @@ def baseline_configs(torch, fp64_peak, hbm_peak):
     sim.dpred(chi)
     sim.Jtvec(chi, v)
     sim.getJtJdiag(chi, W=sp.diags(np.sqrt(0.5 * v)))
-    t_fwd, d = sync_time(lambda: sim.dpred(chi))
-    t_jt, jt = sync_time(lambda: sim.Jtvec(chi, v))
-    t_dg, dg = sync_time(lambda: sim.getJtJdiag(chi, W=sp.diags(np.sqrt(v))))
+    def best_of_two(fn_a, fn_b):
+        (ta, ra), (tb, _) = sync_time(fn_a), sync_time(fn_b)
+        return min(ta, tb), ra
+
+    t_fwd, d = best_of_two(lambda: sim.dpred(chi), lambda: sim.dpred(chi))
+    t_jt, jt = best_of_two(lambda: sim.Jtvec(chi, v), lambda: sim.Jtvec(chi, v))
+    # different weights per call: the sha256 cache of getJtJdiag must not answer
+    t_dg, dg = best_of_two(lambda: sim.getJtJdiag(chi, W=sp.diags(np.sqrt(v))),
+                           lambda: sim.getJtJdiag(chi, W=sp.diags(np.sqrt(0.25 * v))))
     pairs = n_rx * nC
     fe = flop_eq_per_pair(mesh.n_nodes, nC)
     out["cfg3-shard"] = {

@@ -165,6 +165,12 @@ class CudaEngine:
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
+    def copy_stream(self):
+        """Side stream for D2H transfers that overlap with kernels of the compute stream."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = self.torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
     def _workspace(self, nbytes):
         nbytes = max(int(nbytes), 8)
         if self._ws is None or self._ws.numel() * 8 < nbytes:
