@@ -221,6 +221,12 @@ int pf_gemv_t(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype
 int pf_colsumsq(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
                 const double *w, double *d, void *workspace, int64_t workspace_bytes,
                 void *stream);
+/* d += einsum("i,ij,ij->j", w, G, G): accumulating variant (workspace as pf_gemv_t).  pf_gtg_diag uses
+ * it on tensor meshes, where the diagonal is formed a block of receivers at a time from rows the
+ * z-marching kernel writes into scratch memory. */
+int pf_colsumsq_acc(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
+                    const double *w, double *d, void *workspace, int64_t workspace_bytes,
+                    void *stream);
 
 /*
  * Amplitude data (is_amplitude_data=True, magnetics/simulation.py:444-456,

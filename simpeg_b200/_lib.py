@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = (
     "pf_gtg_diag_workspace_bytes", "pf_gtg_diag",
     "pf_gemv_workspace_bytes", "pf_gemv",
     "pf_gemv_t_workspace_bytes", "pf_gemv_t",
-    "pf_colsumsq", "pf_colsumsq_amp",
+    "pf_colsumsq", "pf_colsumsq_acc", "pf_colsumsq_amp",
     "pf_amp_normalize", "pf_amp_combine", "pf_amp_spread",
     "pf_plan_tensor_count", "pf_plan_tensor_fill",
     "pf_probe_fp64_peak",
@@ -122,6 +122,7 @@ def load_library() -> ctypes.CDLL:
         "pf_gemv_t_workspace_bytes": (i64, [i64, i64]),
         "pf_gemv_t": (i32, [vp, i64, i64, i64, i32, vp, vp, vp, i64, vp]),
         "pf_colsumsq": (i32, [vp, i64, i64, i64, i32, vp, vp, vp, i64, vp]),
+        "pf_colsumsq_acc": (i32, [vp, i64, i64, i64, i32, vp, vp, vp, i64, vp]),
         "pf_colsumsq_amp": (i32, [vp, i64, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
         "pf_amp_normalize": (i32, [vp, i64, vp, vp, vp]),
         "pf_amp_combine": (i32, [vp, vp, i64, vp, vp]),

@@ -1667,6 +1667,107 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
 }  // namespace
 
 
+extern "C" int64_t pf_gt_dot_v_workspace_bytes(const pf_plan *plan, const pf_job *job)
+{
+    if (!plan || !job) return -1;
+    int64_t bytes = column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
+    if (plan->n_nodes > 0) {
+        const int rc = choose_rc(pf_ceil_div(plan->n_nodes, PF_THREADS), job->n_receivers, MAX_COLUMN_CHUNKS);
+        const int64_t nchunks = pf_ceil_div(job->n_receivers > 0 ? job->n_receivers : 1, rc);
+        const int64_t node_bytes = (nchunks + 1) * n_blocks_of(job) * plan->n_nodes * (int64_t)sizeof(double);
+        if (node_bytes > bytes) bytes = node_bytes;
+    }
+    return bytes;
+}
+
+extern "C" int pf_gt_dot_v(const pf_plan *plan, const pf_job *job, const double *v, double *result,
+                           void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return column_sink<SINK_GTV>(plan, job, v, result, workspace, workspace_bytes, stream);
+}
+
+// ---- on-the-fly diag(G^T W G) on tensor meshes: blocked build + column norms -----------------
+// The tile kernel needs 1.47 node evaluations per pair (bricks) against 1.10 of the z-marching
+// kernel, but a marching kernel cannot keep per-cell accumulators (it streams the cells).  So the
+// diagonal is formed the way the stored-G path forms it, a block of receivers at a time: the
+// marching kernel writes the block's rows into scratch memory and the HBM-bound column kernel folds
+// sum_i w_i g_ij^2 into the result (24 B written + read per pair at ~7 TB/s against ~400 FP64
+// flop-eq per pair).  Identical arithmetic to pf_build_G + pf_colsumsq.
+namespace {
+constexpr int64_t DIAG_SCRATCH_TARGET = (int64_t)4 << 30;   // recommended scratch (callers may pass more)
+constexpr int64_t DIAG_MIN_RX = 16;
+
+bool diag_blocked(const pf_plan *plan, const pf_job *job)
+{
+    return validate(plan, job) == PF_OK && plan->n_cells > 0 && job->n_receivers > 0 &&
+           pf_job_uses_marching(plan, job, 0) != 0;
+}
+int64_t diag_ld(const pf_plan *plan, const pf_job *job) { return pf_ceil_div(pf_job_columns(plan, job), 16) * 16; }
+}  // namespace
+
+extern "C" int64_t pf_gemv_t_workspace_bytes(int64_t rows, int64_t cols);
+
+namespace {
+// workspace of the column kernel for a block of rb receivers (non-decreasing in rb)
+int64_t diag_column_ws(const pf_plan *plan, const pf_job *job, int64_t rb)
+{
+    return pf_gemv_t_workspace_bytes(rb * job->n_components, pf_job_columns(plan, job));
+}
+}  // namespace
+
+extern "C" int pf_colsumsq_acc(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
+                               const double *w, double *d, void *workspace, int64_t workspace_bytes,
+                               void *stream);
+
+extern "C" int64_t pf_gtg_diag_workspace_bytes(const pf_plan *plan, const pf_job *job)
+{
+    if (!plan || !job) return -1;
+    if (diag_blocked(plan, job)) {
+        const int64_t per_rx = (int64_t)job->n_components * diag_ld(plan, job) * (int64_t)sizeof(double);
+        int64_t rb = DIAG_SCRATCH_TARGET / per_rx;
+        if (rb < DIAG_MIN_RX) rb = DIAG_MIN_RX;
+        if (rb > job->n_receivers) rb = job->n_receivers;
+        return rb * per_rx + diag_column_ws(plan, job, rb);
+    }
+    return column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
+}
+
+extern "C" int pf_gtg_diag(const pf_plan *plan, const pf_job *job, const double *w, double *diag,
+                           void *workspace, int64_t workspace_bytes, void *stream)
+{
+    if (!diag_blocked(plan, job))
+        return column_sink<SINK_DIAG>(plan, job, w, diag, workspace, workspace_bytes, stream);
+    PF_CHECK_ARG(w && diag, "null vector or output");
+    const int64_t nP = pf_job_columns(plan, job), ld = diag_ld(plan, job);
+    const int64_t per_rx = (int64_t)job->n_components * ld * (int64_t)sizeof(double);
+    int64_t rb = workspace ? workspace_bytes / per_rx : 0;
+    if (rb > job->n_receivers) rb = job->n_receivers;
+    for (int it = 0; it < 4 && rb >= 1; ++it) {     // the column workspace shrinks with the block
+        const int64_t fit = (workspace_bytes - diag_column_ws(plan, job, rb)) / per_rx;
+        if (fit >= rb) break;
+        rb = fit;
+    }
+    const int64_t ws2 = rb >= 1 ? diag_column_ws(plan, job, rb) : 0;
+    if (rb < 1) {
+        pf_set_error("pf_gtg_diag: workspace too small");
+        return PF_ERR_WORKSPACE;
+    }
+    char *scratch = (char *)workspace;
+    void *colws = scratch + rb * per_rx;
+    for (int64_t r0 = 0; r0 < job->n_receivers; r0 += rb) {
+        pf_job sub = *job;
+        sub.receivers = job->receivers + 3 * r0;
+        sub.n_receivers = (job->n_receivers - r0 < rb) ? job->n_receivers - r0 : rb;
+        sub.row_offset = 0;
+        int st = pf_build_G(plan, &sub, scratch, ld, PF_F64, stream);
+        if (st != PF_OK) return st;
+        st = pf_colsumsq_acc(scratch, sub.n_receivers * job->n_components, nP, ld, PF_F64,
+                             w + job->row_offset + r0 * job->n_components, diag, colws, ws2, stream);
+        if (st != PF_OK) return st;
+    }
+    return PF_OK;
+}
+
 namespace {
 const char *prog_name(int prog)
 {
@@ -1698,7 +1799,8 @@ extern "C" int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int
     PF_CHECK_ARG(buf && len > 0, "null buffer");
     PF_CHECK_ARG(sink >= SINK_STORE && sink <= SINK_DIAG, "bad sink");
     static thread_local Pass passes[MAX_PASSES];
-    const int n = (sink == SINK_STORE || sink == SINK_FORWARD)
+    const bool blocked_diag = sink == SINK_DIAG && diag_blocked(plan, job);
+    const int n = (sink == SINK_STORE || sink == SINK_FORWARD || blocked_diag)
                       ? make_passes_march(plan, job, passes, sink == SINK_FORWARD)
                       : make_passes(plan, job, passes, MAX_PASSES);
     PF_CHECK_ARG(n >= 0, "component list cannot be scheduled");
@@ -1715,6 +1817,9 @@ extern "C" int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int
                      prog_name(passes[i].prog), sink_name(sink), gt, nr);
         else if (sink == SINK_GTV && plan->n_nodes > 0)
             snprintf(one, sizeof(one), "pf_node_gtv_kernel<%d,%s>", passes[i].family, prog_name(passes[i].prog));
+        else if (sink == SINK_DIAG && blocked_diag)
+            snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,SINK_STORE,double,%d> + column_kernel<double,1>",
+                     passes[i].family, prog_name(passes[i].prog), march_rounds(plan, p, false));
         else
             snprintf(one, sizeof(one), "pf_tile_kernel<%d,%s,%s,%s>", passes[i].family,
                      prog_name(passes[i].prog), sink_name(sink), gt);
@@ -1728,33 +1833,3 @@ extern "C" int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int
     return PF_OK;
 }
 
-extern "C" int64_t pf_gt_dot_v_workspace_bytes(const pf_plan *plan, const pf_job *job)
-{
-    if (!plan || !job) return -1;
-    int64_t bytes = column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
-    if (plan->n_nodes > 0) {
-        const int rc = choose_rc(pf_ceil_div(plan->n_nodes, PF_THREADS), job->n_receivers, MAX_COLUMN_CHUNKS);
-        const int64_t nchunks = pf_ceil_div(job->n_receivers > 0 ? job->n_receivers : 1, rc);
-        const int64_t node_bytes = (nchunks + 1) * n_blocks_of(job) * plan->n_nodes * (int64_t)sizeof(double);
-        if (node_bytes > bytes) bytes = node_bytes;
-    }
-    return bytes;
-}
-
-extern "C" int pf_gt_dot_v(const pf_plan *plan, const pf_job *job, const double *v, double *result,
-                           void *workspace, int64_t workspace_bytes, void *stream)
-{
-    return column_sink<SINK_GTV>(plan, job, v, result, workspace, workspace_bytes, stream);
-}
-
-extern "C" int64_t pf_gtg_diag_workspace_bytes(const pf_plan *plan, const pf_job *job)
-{
-    if (!plan || !job) return -1;
-    return column_chunks(plan, job) * pf_job_columns(plan, job) * (int64_t)sizeof(double);
-}
-
-extern "C" int pf_gtg_diag(const pf_plan *plan, const pf_job *job, const double *w, double *diag,
-                           void *workspace, int64_t workspace_bytes, void *stream)
-{
-    return column_sink<SINK_DIAG>(plan, job, w, diag, workspace, workspace_bytes, stream);
-}

@@ -145,6 +145,17 @@ __global__ void __launch_bounds__(256) reduce_overwrite_kernel(const double *par
     out[i] = t;
 }
 
+// out[i] += sum_c partial[c][i]
+__global__ void __launch_bounds__(256) reduce_add_kernel(const double *partial, int64_t n_parts, int64_t n,
+                                                         double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    for (int64_t c = 0; c < n_parts; ++c) t += partial[c * n + i];
+    out[i] += t;
+}
+
 // ---------------------------------------------------------------------------
 // Column-owner kernels: z = G^T y (MODE 0), d = sum_i w_i G_ij^2 (MODE 1),
 // amplitude d = sum_i w_i (sum_c a_ci G_{3i+c,j})^2 (MODE 2).
@@ -306,14 +317,14 @@ int64_t col_splits(int64_t rows, int64_t cols)
 
 template <typename GT, int MODE>
 int launch_column(const void *G, int64_t rows, int64_t cols, int64_t ld, const double *yv,
-                  const double *amp, double *out, double *ws, cudaStream_t stream)
+                  const double *amp, double *out, double *ws, cudaStream_t stream, bool accumulate = false)
 {
     const int64_t splits = col_splits(rows, cols);
     const int64_t rows_per_split = pf_ceil_div(rows, splits);
     const int64_t used_splits = pf_ceil_div(rows, rows_per_split);
     const int64_t chunks = pf_ceil_div(cols, (int64_t)THREADS * Vec<GT>::N * COL_KC);
     dim3 grid((unsigned)chunks, (unsigned)used_splits);
-    double *target = (used_splits == 1) ? out : ws;
+    double *target = (used_splits == 1 && !accumulate) ? out : ws;
     if (aligned_for_vectors<GT>(G, ld))
         column_kernel<GT, MODE, true><<<grid, THREADS, 0, stream>>>((const GT *)G, rows, cols, ld, yv, amp,
                                                                     rows_per_split, target);
@@ -322,9 +333,13 @@ int launch_column(const void *G, int64_t rows, int64_t cols, int64_t ld, const d
                                                                      rows_per_split, target);
     PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
-    if (used_splits > 1) {
+    if (accumulate) {
+        reduce_add_kernel<<<(unsigned)pf_ceil_div(cols, 256), 256, 0, stream>>>(ws, used_splits, cols, out);
+        PF_COUNT_LAUNCH();
+        PF_CUDA_OK(cudaGetLastError());
+    } else if (used_splits > 1) {
         reduce_overwrite_kernel<<<(unsigned)pf_ceil_div(cols, 256), 256, 0, stream>>>(ws, used_splits, cols, out);
-    PF_COUNT_LAUNCH();
+        PF_COUNT_LAUNCH();
         PF_CUDA_OK(cudaGetLastError());
     }
     return PF_OK;
@@ -456,6 +471,27 @@ extern "C" int pf_colsumsq(const void *G, int64_t rows, int64_t cols, int64_t ld
 {
     return column_entry<1>(G, rows, cols, ld, g_dtype, w, nullptr, d, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+
+// d[k] += sum_i w[i] G[i,k]^2 (accumulating variant: the blocked on-the-fly diagonal of pf_gtg_diag
+// evaluates G a block of receivers at a time into scratch memory and folds every block into d)
+extern "C" int pf_colsumsq_acc(const void *G, int64_t rows, int64_t cols, int64_t ld, int g_dtype,
+                               const double *w, double *d, void *workspace, int64_t workspace_bytes,
+                               void *stream)
+{
+    int st = check_matrix(G, rows, cols, ld, g_dtype);
+    if (st != PF_OK) return st;
+    if (cols == 0 || rows == 0) return PF_OK;
+    PF_CHECK_ARG(w && d, "null vector");
+    if (!workspace || workspace_bytes < pf_gemv_t_workspace_bytes(rows, cols)) {
+        pf_set_error("pf_colsumsq_acc: workspace too small");
+        return PF_ERR_WORKSPACE;
+    }
+    if (g_dtype == PF_F64)
+        return launch_column<double, 1>(G, rows, cols, ld, w, nullptr, d, (double *)workspace,
+                                        (cudaStream_t)stream, true);
+    return launch_column<float, 1>(G, rows, cols, ld, w, nullptr, d, (double *)workspace, (cudaStream_t)stream,
+                                   true);
 }
 
 extern "C" int pf_colsumsq_amp(const void *G, int64_t n_loc, int64_t cols, int64_t ld, int g_dtype,

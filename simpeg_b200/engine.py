@@ -331,7 +331,7 @@ class CudaEngine:
 
     def gtg_diag_dev(self, w_t, out=None):
         """sum_rows w[row] G_local[row, :]**2 without storing G."""
-        self._upload_tiles()
+        self._need_tiles_unless_marching(False)     # tensor meshes: blocked marching build + column norms
         return self._column_sink(self.lib.pf_gtg_diag, self.lib.pf_gtg_diag_workspace_bytes, w_t,
                                  "pf_gtg_diag", out)
 
