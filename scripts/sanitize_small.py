@@ -47,4 +47,23 @@ lay = gravity.SimulationEquivalentSourceLayer(mesh2, top, top - 3.0, survey=sg,
                                               rhoMap=maps.IdentityMap(nP=mesh2.n_cells),
                                               sensitivity_dtype=np.float64)
 lay.dpred(rng.uniform(size=mesh2.n_cells))
+# round 2: derived gzz (receivers on the mesh surface take the exact S-sum path), blocked diag,
+# device CG with a sparse model-map derivative, tile containers
+import scipy.sparse as sp  # noqa: E402
+
+loc0 = loc.copy()
+loc0[:4, 2] = 0.0                                   # on the top face of the mesh ("CCN": top at z = 0)
+loc0[0, :2] = mesh.nodes_x[3], mesh.nodes_y[2]      # exactly on a node
+rxd = gravity.receivers.Point(loc0, components=["gxx", "gyy", "gzz", "gz"])
+sd = gravity.survey.Survey(gravity.sources.SourceField([rxd]))
+for store in ("ram", "forward_only"):
+    simd = gravity.Simulation3DIntegral(mesh, survey=sd, rhoMap=maps.IdentityMap(nP=mesh.n_cells),
+                                        store_sensitivities=store, sensitivity_dtype=np.float64)
+    simd.dpred(rho)
+    simd.getJtJdiag(rho)
+P = sp.random(mesh.n_cells, 40, density=0.1, random_state=1, format="csr")
+simp = gravity.Simulation3DIntegral(mesh, survey=sg, rhoMap=maps.LinearMap(P), sensitivity_dtype=np.float64)
+cgp = DeviceGaussNewtonCG(simp, reg_hessian=np.ones(40), beta=1e-3)
+cgp.set_model(rng.uniform(size=40))
+cgp.find_search_direction(rng.uniform(-1, 1, 40))
 print("sanitize pass done")

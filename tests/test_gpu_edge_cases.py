@@ -157,3 +157,40 @@ def test_store_sensitivities_disk_roundtrip(tmp_path):
     sim3 = gravity.Simulation3DIntegral(mesh, store_sensitivities="ram", **kw32)
     sim3.load_sensitivities()
     assert vec_rel(sim3.dpred(rho), G @ rho) <= 1e-6
+
+
+@pytest.mark.parametrize("components", [["gxx", "gyy", "gzz"], ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"]],
+                         ids=["trace", "cfg2-set"])
+def test_derived_gzz_with_receivers_touching_cells(components):
+    """gzz is derived from gxx and gyy in the z-marching kernel (no plane of its own); the term
+    sum_v s_v S_v it drops is non-zero exactly when the receiver touches a prism.  Receivers on
+    the top face of the mesh -- inside a face, on an edge, on a node -- and one buried inside a
+    cell must still match the oracle (the reference's singular-branch conventions) and the tile
+    kernel, which evaluates kernel_uu at every node."""
+    from simpeg_b200.tiling import build_tile_plan_tensor, tensor_axes_of
+
+    mesh = TensorMesh([[(4.0, 40)], [(5.0, 30)], [(3.0, 12)]], "CCN")
+    xs, ys, zs = mesh.nodes_x, mesh.nodes_y, mesh.nodes_z
+    loc = np.array([
+        [xs[5] + 1.3, ys[4] + 2.1, 0.0],              # inside a top face
+        [xs[16], ys[13] + 1.7, 0.0],                  # on an edge of the top face
+        [xs[27], ys[15], 0.0],                        # on a node of the top face (footprint border row)
+        [xs[2] + 0.9, ys[22] + 1.1, zs[3] + 1.4],     # inside a cell
+        [xs[33], ys[6] + 2.0, zs[7]],                 # on an interior edge
+        [1.234, -2.345, 2.5],                         # ordinary receiver above the mesh
+    ])
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh), None)
+    march = CudaEngine("gravity", None, None, [(loc, components)], plan=plan, use_marching=True)
+    tile = CudaEngine("gravity", None, None, [(loc, components)], plan=plan, use_marching=False)
+    assert "pf_march_kernel" in march.describe("store") and "pf_tile_kernel" in tile.describe("store")
+    ora = OracleSimulation("gravity", mesh.nodes, mesh.cell_nodes, [(loc, components)])
+    G = ora.sensitivity_matrix()
+    march.build_G()
+    tile.build_G()
+    assert rowwise_rel(march.G_to_numpy(), G).max() <= RTOL_NORMWISE
+    assert rowwise_rel(march.G_to_numpy(), tile.G_to_numpy()).max() <= 1e-12
+    m = np.random.default_rng(4).uniform(-0.5, 0.5, mesh.n_cells)
+    assert vec_rel(march.to_host(march.forward_dev(march.to_device(m))), ora.forward(m)) <= RTOL_NORMWISE
+    w = np.random.default_rng(5).uniform(0.5, 1.5, march.n_rows)
+    assert vec_rel(march.to_host(march.gtg_diag_dev(march.to_device(w))),
+                   np.einsum("i,ij,ij->j", w, G, G)) <= RTOL_NORMWISE
