@@ -315,20 +315,16 @@ def march_footprints(nx, ny, nz, ncap, active_index=None):
     number of 256-thread node rounds per layer; rows are
     (ix0, iy0, w, h, iz_begin, iz_end).
     """
-    best = None
-    for a in range(1, nx + 1):
-        w = -(-nx // a)
-        if (w + 1) * 2 > ncap:
-            continue
-        for b in range(1, ny + 1):
-            h = -(-ny // b)
-            if (w + 1) * (h + 1) > ncap:
-                continue
-            cost = a * b * (4 * -(-((w + 1) * (h + 1)) // _ROUND) + -(-(w * h) // _ROUND))
-            key = (cost, a)            # fewer x splits = longer contiguous G runs
-            if best is None or key < best[0]:
-                best = (key, (a, b))
-    a, b = best[1]
+    # all (a, b) splits at once (this runs inside every simulation's first G access)
+    a_all = np.arange(1, nx + 1, dtype=np.int64)[:, None]
+    b_all = np.arange(1, ny + 1, dtype=np.int64)[None, :]
+    w_all, h_all = -(-nx // a_all), -(-ny // b_all)
+    nodes_all = (w_all + 1) * (h_all + 1)
+    cost = (a_all * b_all * (4 * -(-nodes_all // _ROUND) + -(-(w_all * h_all) // _ROUND))).astype(np.float64)
+    cost[(nodes_all > ncap) | ((w_all + 1) * 2 > ncap)] = np.inf
+    # cheapest split; ties: fewer x splits = longer contiguous G runs (then fewer y splits)
+    flat = int(np.argmin(cost))            # row-major argmin = smallest a, then smallest b, among equals
+    a, b = flat // ny + 1, flat % ny + 1
     xb = [nx * i // a for i in range(a + 1)]
     yb = [ny * j // b for j in range(b + 1)]
     fps = []
