@@ -43,7 +43,9 @@ enum { SINK_STORE = 0, SINK_FORWARD = 1, SINK_GTV = 2, SINK_DIAG = 3 };
 // PROG_TMI_*: one component "tmi" (the value is the number of column blocks)
 // PROG_ALL6: family 12 with all six primitives needed (descriptor-driven planes, but the node
 // evaluation is branch-free so the compiler interleaves the five transcendentals)
-enum { PROG_GENERIC = 0, PROG_TMI_SCALAR = 1, PROG_TMI_VECTOR = 3, PROG_ALL6 = 6 };
+// PROG_G1: one first-order gravity component (gx, gy or gz) -- one atan and two logs advanced in
+// lock-step (the generic program evaluates them one after the other behind run-time masks)
+enum { PROG_GENERIC = 0, PROG_TMI_SCALAR = 1, PROG_G1 = 2, PROG_TMI_VECTOR = 3, PROG_ALL6 = 6 };
 #define PF_IS_TMI(P) ((P) == PROG_TMI_SCALAR || (P) == PROG_TMI_VECTOR)
 
 constexpr int MAX_PLANES = 10;
@@ -90,6 +92,7 @@ struct LaunchParams {
     int n_combo;       // planes [n_planes - n_combo, n_planes) are DOT3 / QUAD combinations
     int n_buf;         // marching kernel: 2 = node planes double-buffered (one barrier per layer), 1 = single
     int n_derived;     // outputs [n_out - n_derived, n_out) have no plane (ROLE_DERIVED)
+    int g1_axis;       // PROG_G1: 0 = gx (kernel_e), 1 = gy (kernel_n), 2 = gz (kernel_u)
     PlaneDesc planes[MAX_PLANES];
     OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
@@ -231,6 +234,21 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
             planes[STRIDE + j] = by;
             planes[2 * STRIDE + j] = bz;
         }
+        return;
+    }
+    if (PROG == PROG_G1) {
+        // choclo.prism.kernel_e / kernel_n / kernel_u by cyclic symmetry: for the axis a with the
+        // other two coordinates (b, c) in the reference's order
+        //     k_a = -(b log(c + r) + c log(b + r) - a atan(b c / (a r)))
+        // (kernel_u: a = u, b = e, c = n; kernel_e: a = e, b = n, c = u; kernel_n: a = n, b = u, c = e)
+        const int axis = p.g1_axis;
+        const double a = (axis == 0) ? e : ((axis == 1) ? n : u);
+        const double b = (axis == 0) ? n : ((axis == 1) ? u : e);
+        const double c = (axis == 0) ? u : ((axis == 1) ? e : n);
+        const double r = sqrt(e * e + n * n + u * u);
+        double A, Lc, Lb;
+        pf_node_atan1_log2(a, b, c, r, A, Lc, Lb);
+        planes[j] = -(b * Lc + c * Lb - a * A);
         return;
     }
     eval_raw<FAM>((PROG == PROG_ALL6) ? (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU) : p.need,
@@ -1261,6 +1279,11 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
         else if (passes[i].family == 12 &&
                  p.need == (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU))
             passes[i].prog = PROG_ALL6;
+        else if (passes[i].family == 12 && job->physics == PF_GRAVITY && p.n_out == 1 && p.n_planes == 1 &&
+                 p.planes[0].kind == PK_RAW && p.planes[0].q[0] >= Q_E && p.planes[0].q[0] <= Q_U) {
+            passes[i].prog = PROG_G1;
+            p.g1_axis = p.planes[0].q[0] - Q_E;
+        }
     }
     return n;
 }
@@ -1305,6 +1328,7 @@ int launch_pass(const Pass &pass, cudaStream_t stream)
         if (pass.prog == PROG_TMI_SCALAR)
             return launch_tile_kernel<12, PROG_TMI_SCALAR, SINK, GT>(pass.p, stream);
         if (pass.prog == PROG_ALL6) return launch_tile_kernel<12, PROG_ALL6, SINK, GT>(pass.p, stream);
+        if (pass.prog == PROG_G1) return launch_tile_kernel<12, PROG_G1, SINK, GT>(pass.p, stream);
         return launch_tile_kernel<12, PROG_GENERIC, SINK, GT>(pass.p, stream);
     }
     return launch_tile_kernel<3, PROG_GENERIC, SINK, GT>(pass.p, stream);
@@ -1377,6 +1401,8 @@ int launch_march_nr(const Pass &pass, cudaStream_t stream)
             return launch_march_kernel<12, PROG_TMI_SCALAR, SINK, GT, NR>(pass.p, stream);
         if (pass.prog == PROG_ALL6)
             return launch_march_kernel<12, PROG_ALL6, SINK, GT, NR>(pass.p, stream);
+        if (pass.prog == PROG_G1)
+            return launch_march_kernel<12, PROG_G1, SINK, GT, NR>(pass.p, stream);
         return launch_march_kernel<12, PROG_GENERIC, SINK, GT, NR>(pass.p, stream);
     }
     return launch_march_kernel<3, PROG_GENERIC, SINK, GT, NR>(pass.p, stream);
@@ -1629,6 +1655,7 @@ int column_sink(const pf_plan *plan, const pf_job *job, const double *vec, doubl
             else if (passes[i].prog == PROG_TMI_VECTOR) PF_LAUNCH_NODE(12, PROG_TMI_VECTOR);
             else if (passes[i].prog == PROG_TMI_SCALAR) PF_LAUNCH_NODE(12, PROG_TMI_SCALAR);
             else if (passes[i].prog == PROG_ALL6) PF_LAUNCH_NODE(12, PROG_ALL6);
+            else if (passes[i].prog == PROG_G1) PF_LAUNCH_NODE(12, PROG_G1);
             else PF_LAUNCH_NODE(12, PROG_GENERIC);
 #undef PF_LAUNCH_NODE
             PF_COUNT_LAUNCH();
@@ -1775,6 +1802,7 @@ const char *prog_name(int prog)
     case PROG_TMI_SCALAR: return "PROG_TMI_SCALAR";
     case PROG_TMI_VECTOR: return "PROG_TMI_VECTOR";
     case PROG_ALL6: return "PROG_ALL6";
+    case PROG_G1: return "PROG_G1";
     default: return "PROG_GENERIC";
     }
 }
