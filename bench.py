@@ -378,8 +378,13 @@ def dev_ms(torch, fn, reps=3):
 
 
 # --------------------------------------------------------------------------- other BASELINE configs
-def flop_eq_per_pair(n_nodes, n_cells):
-    return FLOP_EQ_PER_NODE * n_nodes / n_cells + FLOP_EQ_PER_CELL
+# SURVEY.md 8(d) bookkeeping per kernel set: (flop-eq per node, flop-eq per cell)
+FLOP_EQ = {"second_order": (339.0, 64.0), "gz_only": (177.0, 8.0), "gravity7": (339.0, 69.0)}
+
+
+def flop_eq_per_pair(n_nodes, n_cells, kind="second_order"):
+    per_node, per_cell = FLOP_EQ[kind]
+    return per_node * n_nodes / n_cells + per_cell
 
 
 def baseline_configs(torch, fp64_peak, hbm_peak):
@@ -425,7 +430,8 @@ def baseline_configs(torch, fp64_peak, hbm_peak):
         "what": "gravity gz forward + getJ, TensorMesh 40x40x20, 441 receivers, store='ram' (full config)",
         "build_pairs_s": wl["n_rx"] * nC / t_build * 1e3, "ms_build": t_build,
         "kernel": sim._dev.describe("store"),
-        "frac_fp64": wl["n_rx"] * nC / t_build * 1e3 * flop_eq_per_pair(wl["mesh"].n_nodes, nC) / fp64_peak,
+        "frac_fp64": wl["n_rx"] * nC / t_build * 1e3 * flop_eq_per_pair(wl["mesh"].n_nodes, nC, "gz_only") / fp64_peak,
+        "flop_eq_per_pair": flop_eq_per_pair(wl["mesh"].n_nodes, nC, "gz_only"),
         "parity": max(_rel(np.asarray(J)[pos], Gs), _rel(sim.dpred(rho)[pos], Gs @ rho)),
         "getJ_is_ndarray": isinstance(J, np.ndarray),
     }
@@ -454,7 +460,8 @@ def baseline_configs(torch, fp64_peak, hbm_peak):
                 "(8750 rows, 35 GB fp64 G): one-pass build + Jvec/Jtvec",
         "build_pairs_s": wl["n_rx"] * nC / t_build * 1e3, "ms_build": t_build,
         "kernel": eng.describe("store"),
-        "frac_fp64": wl["n_rx"] * nC / t_build * 1e3 * flop_eq_per_pair(wl["mesh"].n_nodes, nC) / fp64_peak,
+        "frac_fp64": wl["n_rx"] * nC / t_build * 1e3 * flop_eq_per_pair(wl["mesh"].n_nodes, nC, "gravity7") / fp64_peak,
+        "flop_eq_per_pair": flop_eq_per_pair(wl["mesh"].n_nodes, nC, "gravity7"),
         "jvec_jtvec_gbs": 2 * g_bytes / t_prod / 1e6, "frac_hbm": 2 * g_bytes / t_prod / 1e6 / hbm_peak,
         "parity": float(np.max(np.max(np.abs(Gd - Gs), axis=1) / np.max(np.abs(Gs), axis=1))),
     }
@@ -558,7 +565,9 @@ def baseline_configs(torch, fp64_peak, hbm_peak):
         "cells": nC, "mesh_s": t_mesh, "plan_upload_s": t_plan, "tiles": int(eng.host_plan.n_tiles),
         "build_pairs_s": n_rx * nC / t_build2, "ms_build": 1e3 * t_build2, "first_build_s": t_build,
         "kernel": eng.describe("store"),
-        "frac_fp64": n_rx * nC / t_build2 * flop_eq_per_pair(nodes.shape[0], nC) / fp64_peak,
+        "frac_fp64": n_rx * nC / t_build2 * flop_eq_per_pair(nodes.shape[0], nC, "gz_only") / fp64_peak,
+        "flop_eq_per_pair": flop_eq_per_pair(nodes.shape[0], nC, "gz_only"),   # unique nodes, not tile slots
+        "node_evaluations_per_pair": float(eng.host_plan.nodes_per_cell),
         "getJtJdiag_gbs": g_bytes / t_diag / 1e9, "frac_hbm_getJtJdiag": g_bytes / t_diag / 1e9 / hbm_peak,
         "cg_ms_per_iteration": 1e3 * t_cg / max(solver.cg_count, 1),
         "cg_jvec_jtvec_gbs": 2 * g_bytes * solver.cg_count / t_cg / 1e9,

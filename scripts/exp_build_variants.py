@@ -51,6 +51,11 @@ def one():
         ("grav_gz_100^3", (100, 100, 100), 10.0, "gravity", ["gz"], "scalar", 2500),
         ("grav_7comp_100x100x50", (100, 100, 50), 10.0, "gravity",
          ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"], "scalar", 1250),
+        ("tmideriv3_scalar_100^3", (100, 100, 100), 10.0, "magnetics", ["tmi_x", "tmi_y", "tmi_z"], "scalar", 1000),
+        ("maggrad6_scalar_100x100x50", (100, 100, 50), 10.0, "magnetics",
+         ["bxx", "bxy", "bxz", "byy", "byz", "bzz"], "scalar", 1000),
+        ("bx_scalar_100^3", (100, 100, 100), 10.0, "magnetics", ["bx"], "scalar", 2000),
+        ("gzz_100^3", (100, 100, 100), 10.0, "gravity", ["gzz"], "scalar", 2500),
     ]
     only = os.environ.get("PF_EXP_CASES")
     out = {"lib": os.environ.get("PF_CUDA_LIB", "default")}

@@ -47,6 +47,10 @@ enum { SINK_STORE = 0, SINK_FORWARD = 1, SINK_GTV = 2, SINK_DIAG = 3 };
 // lock-step (the generic program evaluates them one after the other behind run-time masks)
 enum { PROG_GENERIC = 0, PROG_TMI_SCALAR = 1, PROG_G1 = 2, PROG_TMI_VECTOR = 3, PROG_ALL6 = 6 };
 #define PF_IS_TMI(P) ((P) == PROG_TMI_SCALAR || (P) == PROG_TMI_VECTOR)
+// programs whose outputs are known at compile time: output o = plane o = column block o of the one
+// component, one common factor (PF_NOUT of them)
+#define PF_FIXED(P) (PF_IS_TMI(P) || (P) == PROG_G1)
+#define PF_NOUT(P) ((P) == PROG_TMI_VECTOR ? 3 : 1)
 
 constexpr int MAX_PLANES = 10;
 constexpr int MAX_OUT = 32;
@@ -93,6 +97,10 @@ struct LaunchParams {
     int n_buf;         // marching kernel: 2 = node planes double-buffered (one barrier per layer), 1 = single
     int n_derived;     // outputs [n_out - n_derived, n_out) have no plane (ROLE_DERIVED)
     int g1_axis;       // PROG_G1: 0 = gx (kernel_e), 1 = gy (kernel_n), 2 = gz (kernel_u)
+    // combination planes (DOT3 / QUAD) as linear combinations of the ten raw node kernels:
+    // value = sum_q combo_coef[s][q] k[q] over the bits of combo_mask[s] (filled by make_passes)
+    int combo_mask[MAX_PLANES];
+    double combo_coef[MAX_PLANES][10];
     PlaneDesc planes[MAX_PLANES];
     OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
@@ -107,22 +115,6 @@ struct LaunchParams {
 struct Raw10 {
     double v0, v1, v2, v3, v4, v5, v6, v7, v8, v9;
 };
-
-__device__ __forceinline__ double pick(const Raw10 &k, int q)
-{
-    switch (q) {
-    case 0: return k.v0;
-    case 1: return k.v1;
-    case 2: return k.v2;
-    case 3: return k.v3;
-    case 4: return k.v4;
-    case 5: return k.v5;
-    case 6: return k.v6;
-    case 7: return k.v7;
-    case 8: return k.v8;
-    default: return k.v9;
-    }
-}
 
 // choclo.prism third-order kernels (restated, see oracle/pf_oracle.c)
 __device__ __forceinline__ double kernel_iii(double xi, double xj, double xk, double r)
@@ -162,6 +154,17 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
             pf_node_atan2_log3(e, n, u, r, Aee, Ann, Len, Leu, Lnu);
             need = NEED_AUU;
         }
+        // one atan + the two logs of the same axis (bx / by / bz, gx / gy / gz): lock-step as well
+        if (need == (NEED_AEE | NEED_LEN | NEED_LEU)) {
+            pf_node_atan1_log2(e, n, u, r, Aee, Len, Leu);
+            need = 0;
+        } else if (need == (NEED_ANN | NEED_LEN | NEED_LNU)) {
+            pf_node_atan1_log2(n, u, e, r, Ann, Lnu, Len);
+            need = 0;
+        } else if (need == (NEED_AUU | NEED_LEU | NEED_LNU)) {
+            pf_node_atan1_log2(u, e, n, r, Auu, Leu, Lnu);
+            need = 0;
+        }
         if (need & NEED_AEE) Aee = pf_safe_atan2(n * u, e * r);
         if (need & NEED_ANN) Ann = pf_safe_atan2(e * u, n * r);
 #ifndef PF_NO_ATAN_IDENTITY
@@ -197,6 +200,47 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
         k.v9 = 0.5 * ((-Ann) - (-Aee));
     } else {
         k.v0 = k.v1 = k.v2 = k.v3 = k.v4 = k.v5 = k.v6 = k.v7 = k.v8 = k.v9 = 0.0;
+        if (need == 0x3ff) {
+            // all ten third-order kernels (tmi_x/y/z, the gradient tensor): straight-line, so that
+            // the seven reciprocal refinements and ten quotients interleave.  The six kernel_iij
+            // share three denominators (x_k + r) r; per kernel the operations are those of
+            // kernel_iii / kernel_iij with pf_div (same bits).
+            const double e2 = e * e, n2 = n * n, u2 = u * u;
+            const double s_en = e2 + n2, s_eu = e2 + u2, s_nu = n2 + u2;
+            const double d_e = s_en * s_eu * r, d_n = s_nu * s_en * r, d_u = s_eu * s_nu * r;
+            const double m_e = -n * u * (2 * e2 + n2 + u2);
+            const double m_n = -u * e * (2 * n2 + u2 + e2);
+            const double m_u = -e * n * (2 * u2 + e2 + n2);
+            const double g_u = (u + r) * r, g_n = (n + r) * r, g_e = (e + r) * r;
+            const double den[7] = {d_e, d_n, d_u, g_u, g_n, g_e, r};
+            double rc[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) rc[i] = pf_rcp_approx(den[i]);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { const double t = fma(-den[i], rc[i], 1.0); rc[i] = fma(rc[i], t, rc[i]); }
+            const double num[10] = {m_e, m_n, m_u, -e, -e, -n, -n, -u, -u, 1.0};
+            const int which[10] = {0, 1, 2, 3, 4, 3, 5, 4, 5, 6};
+            double q[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) q[i] = num[i] * rc[which[i]];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const double rem = fma(-den[which[i]], q[i], num[i]);
+                q[i] = fma(rem, rc[which[i]], q[i]);
+            }
+            const bool ze = e == 0.0, zn = n == 0.0, zu = u == 0.0;
+            k.v0 = ((ze && zn) || (ze && zu)) ? 0.0 : q[0];   // eee = iii(e, n, u)
+            k.v1 = ((zn && zu) || (zn && ze)) ? 0.0 : q[1];   // nnn = iii(n, u, e)
+            k.v2 = ((zu && ze) || (zu && zn)) ? 0.0 : q[2];   // uuu = iii(u, e, n)
+            k.v3 = (ze && zn && u < 0.0) ? 0.0 : q[3];        // een = iij(e, n, u)
+            k.v4 = (ze && zu && n < 0.0) ? 0.0 : q[4];        // eeu = iij(e, u, n)
+            k.v5 = (zn && ze && u < 0.0) ? 0.0 : q[5];        // enn = iij(n, e, u)
+            k.v6 = (zn && zu && e < 0.0) ? 0.0 : q[6];        // nnu = iij(n, u, e)
+            k.v7 = (zu && ze && n < 0.0) ? 0.0 : q[7];        // euu = iij(u, e, n)
+            k.v8 = (zu && zn && e < 0.0) ? 0.0 : q[8];        // nuu = iij(u, n, e)
+            k.v9 = (r == 0.0) ? 0.0 : -q[9];                  // enu = -1 / r
+            return;
+        }
         if (need & (1 << T_EEE)) k.v0 = kernel_iii(e, n, u, r);
         if (need & (1 << T_NNN)) k.v1 = kernel_iii(n, u, e, r);
         if (need & (1 << T_UUU)) k.v2 = kernel_iii(u, e, n, r);
@@ -262,19 +306,17 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         PF_RAW(5, k.v5) PF_RAW(6, k.v6) PF_RAW(7, k.v7) PF_RAW(8, k.v8) PF_RAW(9, k.v9)
 #undef PF_RAW
     }
+    // combination planes: k . f (DOT3) and f^T K f (QUAD) are linear in the raw kernels, so each is
+    // a short chain of DFMAs with uniform coefficients (predicated on a uniform mask) -- no run-time
+    // selection of kernel values (the former pick() switches cost more than the kernels themselves)
     for (int s = p.n_planes - p.n_combo; s < p.n_planes; ++s) {   // raw planes come first
-        const PlaneDesc &pd = p.planes[s];
-        double val;
-        if (pd.kind == PK_DOT3) {
-            val = pick(k, pd.q[0]) * fx + pick(k, pd.q[1]) * fy + pick(k, pd.q[2]) * fz;
-        } else {
-            const double kxx = pick(k, pd.q[0]), kyy = pick(k, pd.q[1]), kzz = pick(k, pd.q[2]);
-            const double kxy = pick(k, pd.q[3]), kxz = pick(k, pd.q[4]), kyz = pick(k, pd.q[5]);
-            const double bx = kxx * fx + kxy * fy + kxz * fz;
-            const double by = kxy * fx + kyy * fy + kyz * fz;
-            const double bz = kxz * fx + kyz * fy + kzz * fz;
-            val = bx * fx + by * fy + bz * fz;
-        }
+        const double *c = p.combo_coef[s];
+        const int m = p.combo_mask[s];
+        double val = 0.0;
+#define PF_TERM(q, v) if (m & (1 << q)) val = fma(c[q], (v), val);
+        PF_TERM(0, k.v0) PF_TERM(1, k.v1) PF_TERM(2, k.v2) PF_TERM(3, k.v3) PF_TERM(4, k.v4)
+        PF_TERM(5, k.v5) PF_TERM(6, k.v6) PF_TERM(7, k.v7) PF_TERM(8, k.v8) PF_TERM(9, k.v9)
+#undef PF_TERM
         planes[s * STRIDE + j] = val;
     }
 }
@@ -331,7 +373,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
     const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
     const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
     const int64_t nC = p.plan.n_cells;
-    const int nblk = PF_IS_TMI(PROG) ? PROG : p.nblk;
+    const int nblk = PF_FIXED(PROG) ? PF_NOUT(PROG) : p.nblk;
 
     // ---- tile-stationary state ------------------------------------------------
     const int nn = p.plan.tile_n_nodes[tile];
@@ -370,7 +412,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
 
         // ---- phase 2: cells ---------------------------------------------------
         const char *pbase = reinterpret_cast<const char *>(planes);
-        if (PF_IS_TMI(PROG)) {
+        if (PF_FIXED(PROG)) {
             // single component: row = row_offset + r, factor of the only component
             const int64_t row = p.row_offset + r * p.n_comp_total + p.outs[0].ci;
             const double factor = p.outs[0].factor;
@@ -382,7 +424,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
             for (int s = 0; s < PF_CPT; ++s) {
                 if (col[s] < 0) continue;
 #pragma unroll
-                for (int b = 0; b < PROG; ++b) {
+                for (int b = 0; b < PF_NOUT(PROG); ++b) {
                     const double g = factor * vertex_sum(pbase + b * PLANE_BYTES, verts[s]);
                     if (SINK == SINK_STORE) grow[(unsigned)col[s] + (uint64_t)b * nC] = (GT)g;
                     else if (SINK == SINK_FORWARD) fsum += g * mdl[s][b];
@@ -494,9 +536,9 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     constexpr int LAYER_BYTES = NCAP * 8;
     extern __shared__ double smem[];
     const int n_planes = p.n_planes;
-    const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
+    const int n_out = PF_FIXED(PROG) ? PF_NOUT(PROG) : p.n_out;
     // outputs [0, n_plain) read a plane and own a dprev slot; [n_plain, n_out) are derived
-    const int n_plain = PF_IS_TMI(PROG) ? PROG : p.n_out - p.n_derived;
+    const int n_plain = PF_FIXED(PROG) ? PF_NOUT(PROG) : p.n_out - p.n_derived;
     const int buf_doubles = n_planes * NCAP;
     const int n_buf = p.n_buf;    // 1 when two buffers would not leave room for 3 CTAs per SM
     double *dprev = smem + n_buf * (size_t)buf_doubles;       // [n_plain][NR][THREADS] corner differences
@@ -519,8 +561,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const int64_t nC = p.plan.n_cells;
     const int64_t layer_stride = (int64_t)nx * ny;
     const int sW = W1 * 8;  // byte stride of one node row inside a layer plane
-    const bool direct = PF_IS_TMI(PROG) || p.direct;
-    const bool has_derived = !PF_IS_TMI(PROG) && n_out > n_plain;
+    const bool direct = PF_FIXED(PROG) || p.direct;
+    const bool has_derived = !PF_FIXED(PROG) && n_out > n_plain;
 
     // ---- footprint-stationary state -------------------------------------------
     double x[NR], y[NR];
@@ -704,10 +746,10 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 }
             }
             double fsum = 0.0;
-            if constexpr (PF_IS_TMI(PROG)) {
+            if constexpr (PF_FIXED(PROG)) {
                 // one component, PROG outputs = planes = column blocks (block o at o * nC), one
                 // factor: slot-major, all addresses of a slot derived once (immediate offsets)
-                constexpr int NO = PROG;
+                constexpr int NO = PF_NOUT(PROG);
                 const double factor = s_fac[0];
                 const unsigned long long dst0 = s_dst[0];
                 const int64_t blk_bytes = nC * (int64_t)((SINK == SINK_STORE) ? sizeof(GT) : sizeof(double));
@@ -770,9 +812,9 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 for (int o = 0; o < MAX_PLANES; ++o) {
                     if (o >= n_out) break;
                     PF_PHASE2_BODY(o, o * LAYER_BYTES)
-                    if (SINK == SINK_FORWARD && emit && (PF_IS_TMI(PROG) ? (o == n_out - 1) : p.outs[o].last)) {
+                    if (SINK == SINK_FORWARD && emit && (PF_FIXED(PROG) ? (o == n_out - 1) : p.outs[o].last)) {
                         fsum = warp_sum(fsum);
-                        const int fi = PF_IS_TMI(PROG) ? 0 : p.outs[o].fi;
+                        const int fi = PF_FIXED(PROG) ? 0 : p.outs[o].fi;
                         if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd + fi] += fsum;
                         fsum = 0.0;
                     }
@@ -848,8 +890,8 @@ __global__ void __launch_bounds__(PF_THREADS, 3)
     const double x = p.plan.node_xyz[jj];
     const double y = p.plan.node_xyz[n_nodes + jj];
     const double z = p.plan.node_xyz[2 * n_nodes + jj];
-    const int nblk = PF_IS_TMI(PROG) ? PROG : p.nblk;
-    const int n_out = PF_IS_TMI(PROG) ? PROG : p.n_out;
+    const int nblk = PF_FIXED(PROG) ? PF_NOUT(PROG) : p.nblk;
+    const int n_out = PF_FIXED(PROG) ? PF_NOUT(PROG) : p.n_out;
     const int64_t r_begin = (int64_t)blockIdx.y * p.rc;
     const int64_t r_end = min(r_begin + (int64_t)p.rc, p.n_receivers);
     double a0 = 0, a1 = 0, a2 = 0, c0 = 0, c1 = 0, c2 = 0;   // Kahan sums per column block
@@ -862,8 +904,8 @@ __global__ void __launch_bounds__(PF_THREADS, 3)
             const OutDesc &od = p.outs[o];
             const int64_t row = p.row_offset + r * p.n_comp_total + od.ci;
             const double coef = __ldg(p.vec + row) * od.factor;
-            const int plane = PF_IS_TMI(PROG) ? o : od.plane;
-            const int blk = PF_IS_TMI(PROG) ? o : od.blk;
+            const int plane = PF_FIXED(PROG) ? o : od.plane;
+            const int blk = PF_FIXED(PROG) ? o : od.blk;
             const double term = coef * vals[plane * PF_THREADS + tid];
             if (blk == 0) { const double yk = term - c0, t = a0 + yk; c0 = (t - a0) - yk; a0 = t; }
             else if (blk == 1) { const double yk = term - c1, t = a1 + yk; c1 = (t - a1) - yk; a1 = t; }
@@ -1208,6 +1250,26 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
                     p.n_combo++;
                 }
             for (int sl = 0; sl < p.n_planes; ++sl) p.planes[sl] = sorted[sl];
+            for (int sl = 0; sl < p.n_planes; ++sl) {
+                const PlaneDesc &pd = p.planes[sl];
+                p.combo_mask[sl] = 0;
+                for (int q = 0; q < 10; ++q) p.combo_coef[sl][q] = 0.0;
+                const double f[3] = {p.fx, p.fy, p.fz};
+                if (pd.kind == PK_DOT3) {
+                    for (int a = 0; a < 3; ++a) p.combo_coef[sl][pd.q[a]] += f[a];
+                } else if (pd.kind == PK_QUAD) {
+                    // f^T K f with K = (xx, yy, zz, xy, xz, yz) = k[q0..q5]
+                    p.combo_coef[sl][pd.q[0]] += f[0] * f[0];
+                    p.combo_coef[sl][pd.q[1]] += f[1] * f[1];
+                    p.combo_coef[sl][pd.q[2]] += f[2] * f[2];
+                    p.combo_coef[sl][pd.q[3]] += 2.0 * f[0] * f[1];
+                    p.combo_coef[sl][pd.q[4]] += 2.0 * f[0] * f[2];
+                    p.combo_coef[sl][pd.q[5]] += 2.0 * f[1] * f[2];
+                }
+                if (pd.kind != PK_RAW)
+                    for (int q = 0; q < 10; ++q)
+                        if (p.combo_coef[sl][q] != 0.0) p.combo_mask[sl] |= 1 << q;
+            }
             for (int o = 0; o < p.n_out; ++o) p.outs[o].plane = new_of_old[p.outs[o].plane];
             // one plane per output: order the outputs by plane (phase 2 then reads plane o for
             // output o with compile-time offsets) if every component's outputs stay contiguous
