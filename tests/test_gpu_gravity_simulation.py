@@ -179,3 +179,24 @@ def test_inactive_cells():
     ora = oracle_for(sim)
     assert vec_rel(sim.dpred(rho), ora.forward(rho)) <= RTOL_NORMWISE
     assert rowwise_rel(sim.G.to_numpy(), ora.sensitivity_matrix()).max() <= RTOL_NORMWISE
+
+
+def test_user_supplied_G_is_uploaded_not_evaluated():
+    # LinearSimulation(G=...) / ``sim.G = array`` (simpeg/simulation.py:664-665, 684-688): the matrix
+    # handed in is what the products use
+    sim, mesh, rho, model = make_sim(["gz", "gzz"], "ram")
+    rng = np.random.default_rng(12)
+    G = rng.normal(size=(sim.survey.nD, mesh.n_cells))
+    other = gravity.Simulation3DIntegral(mesh, survey=sim.survey, rhoMap=sim.rhoMap, G=G,
+                                         sensitivity_dtype=np.float64, counter=None, verbose=False)
+    v = rng.normal(size=sim.survey.nD)
+    assert vec_rel(other.dpred(model), G @ rho) <= 1e-13
+    assert vec_rel(other.Jtvec(model, v), G.T @ v) <= 1e-13
+    np.testing.assert_allclose(other.getJ(model), G)
+    # assigning G afterwards replaces the resident matrix
+    sim.dpred(model)
+    sim.G = 2.0 * G
+    assert vec_rel(sim.dpred(model), 2.0 * (G @ rho)) <= 1e-13
+    with pytest.raises(ValueError, match="G must have shape"):
+        bad = gravity.Simulation3DIntegral(mesh, survey=sim.survey, rhoMap=sim.rhoMap, G=G[:, :-1])
+        bad.dpred(model)
