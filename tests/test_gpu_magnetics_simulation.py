@@ -186,3 +186,21 @@ def test_unsupported_component_set():
                                          chi=np.zeros(64))
     with pytest.raises(NotImplementedError, match="aren't implemented yet"):
         sim.dpred(np.zeros(64))
+
+
+def test_jtvec_in_column_slabs_with_overlapped_d2h(monkeypatch):
+    """The host-vector Jtvec runs the column kernel in slabs and fetches finished slabs on a copy
+    stream while the next one computes (production sizes only by default): force it on a small
+    problem and compare with the oracle, fp64 and fp32 storage."""
+    from simpeg_b200.potential_fields import base
+
+    monkeypatch.setattr(base, "JTVEC_SLABS", 3)
+    monkeypatch.setattr(base, "JTVEC_SLAB_ALIGN", 16)
+    monkeypatch.setattr(base, "JTVEC_SLAB_MIN", 32)
+    for dtype, tol in ((np.float64, RTOL_NORMWISE), (np.float32, 1e-6)):
+        sim, mesh, chi, model = make_sim(["tmi", "bx"], "vector", "ram", "identity_map", dtype=dtype)
+        assert len(base.column_slabs(sim._n_columns(), 3)) == 3
+        G = oracle_for(sim).sensitivity_matrix()
+        w = np.random.default_rng(8).uniform(size=sim.survey.nD)
+        assert vec_rel(sim.Jtvec(model, w), G.T @ w) <= tol
+        assert vec_rel(sim.Jtvec(model, 2.0 * w), 2.0 * (G.T @ w)) <= tol     # buffers are reused safely

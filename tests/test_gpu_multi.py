@@ -33,6 +33,8 @@ def _worker(rank, world, port, out_dir):
         from simpeg_b200.potential_fields import base, magnetics
 
         base.SLICED_UPLOAD_MIN = 0      # exercise the rank-sliced upload + all-gather of model vectors
+        # ... and the slab-overlapped Jtvec (column slabs, async all-reduce per slab, D2H on a copy stream)
+        base.JTVEC_SLABS, base.JTVEC_SLAB_ALIGN, base.JTVEC_SLAB_MIN = 3, 16, 32
 
         mesh = small_mesh()
         out = {}
