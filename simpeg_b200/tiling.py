@@ -315,16 +315,22 @@ def march_footprints(nx, ny, nz, ncap, active_index=None):
     number of 256-thread node rounds per layer; rows are
     (ix0, iy0, w, h, iz_begin, iz_end).
     """
-    # all (a, b) splits at once (this runs inside every simulation's first G access)
-    a_all = np.arange(1, nx + 1, dtype=np.int64)[:, None]
-    b_all = np.arange(1, ny + 1, dtype=np.int64)[None, :]
-    w_all, h_all = -(-nx // a_all), -(-ny // b_all)
-    nodes_all = (w_all + 1) * (h_all + 1)
-    cost = (a_all * b_all * (4 * -(-nodes_all // _ROUND) + -(-(w_all * h_all) // _ROUND))).astype(np.float64)
-    cost[(nodes_all > ncap) | ((w_all + 1) * 2 > ncap)] = np.inf
-    # cheapest split; ties: fewer x splits = longer contiguous G runs (then fewer y splits)
-    flat = int(np.argmin(cost))            # row-major argmin = smallest a, then smallest b, among equals
-    a, b = flat // ny + 1, flat % ny + 1
+    # every (a, b) split: vectorised over b, one short numpy pass per a (this runs inside every
+    # simulation's first G access; memory stays O(ny) for any mesh size)
+    b_all = np.arange(1, ny + 1, dtype=np.int64)
+    h_all = -(-ny // b_all)
+    best = None
+    for a in range(1, nx + 1):
+        w = -(-nx // a)
+        if (w + 1) * 2 > ncap:
+            continue
+        nodes_all = (w + 1) * (h_all + 1)
+        cost = (a * b_all * (4 * -(-nodes_all // _ROUND) + -(-(w * h_all) // _ROUND))).astype(np.float64)
+        cost[nodes_all > ncap] = np.inf
+        j = int(np.argmin(cost))               # first minimum = smallest b among equals
+        if np.isfinite(cost[j]) and (best is None or cost[j] < best[0]):
+            best = (float(cost[j]), a, j + 1)  # strict <: ties keep the smaller a (longer G runs)
+    _, a, b = best
     xb = [nx * i // a for i in range(a + 1)]
     yb = [ny * j // b for j in range(b + 1)]
     fps = []
