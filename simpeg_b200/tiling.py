@@ -315,21 +315,22 @@ def march_footprints(nx, ny, nz, ncap, active_index=None):
     number of 256-thread node rounds per layer; rows are
     (ix0, iy0, w, h, iz_begin, iz_end).
     """
-    # every (a, b) split: vectorised over b, one short numpy pass per a (this runs inside every
-    # simulation's first G access; memory stays O(ny) for any mesh size)
-    b_all = np.arange(1, ny + 1, dtype=np.int64)
+    # every (a, b) split (this runs inside every simulation's first G access): one numpy pass over
+    # the whole (a, b) table for ordinary meshes, row blocks of it for huge ones (bounded memory)
+    b_all = np.arange(1, ny + 1, dtype=np.int64)[None, :]
     h_all = -(-ny // b_all)
+    rows_per_block = max(1, (1 << 20) // ny)
     best = None
-    for a in range(1, nx + 1):
-        w = -(-nx // a)
-        if (w + 1) * 2 > ncap:
-            continue
-        nodes_all = (w + 1) * (h_all + 1)
-        cost = (a * b_all * (4 * -(-nodes_all // _ROUND) + -(-(w * h_all) // _ROUND))).astype(np.float64)
-        cost[nodes_all > ncap] = np.inf
-        j = int(np.argmin(cost))               # first minimum = smallest b among equals
-        if np.isfinite(cost[j]) and (best is None or cost[j] < best[0]):
-            best = (float(cost[j]), a, j + 1)  # strict <: ties keep the smaller a (longer G runs)
+    for a0 in range(1, nx + 1, rows_per_block):
+        a_blk = np.arange(a0, min(a0 + rows_per_block, nx + 1), dtype=np.int64)[:, None]
+        w_blk = -(-nx // a_blk)
+        nodes_all = (w_blk + 1) * (h_all + 1)
+        cost = (a_blk * b_all * (4 * -(-nodes_all // _ROUND) + -(-(w_blk * h_all) // _ROUND))).astype(np.float64)
+        cost[(nodes_all > ncap) | ((w_blk + 1) * 2 > ncap)] = np.inf
+        flat = int(np.argmin(cost))            # row-major: smallest a, then smallest b, among equals
+        c = float(cost.flat[flat])
+        if np.isfinite(c) and (best is None or c < best[0]):
+            best = (c, a0 + flat // ny, flat % ny + 1)   # strict <: ties keep the smaller a (longer G runs)
     _, a, b = best
     xb = [nx * i // a for i in range(a + 1)]
     yb = [ny * j // b for j in range(b + 1)]
