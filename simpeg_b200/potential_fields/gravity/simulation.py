@@ -12,7 +12,7 @@ from __future__ import annotations
 import hashlib
 
 import numpy as np
-from scipy.sparse.linalg import LinearOperator, aslinearoperator
+from scipy.sparse.linalg import LinearOperator
 
 from ..base import BaseEquivalentSourceLayerSimulation, BasePFSimulation
 

@@ -13,7 +13,7 @@ from __future__ import annotations
 import hashlib
 
 import numpy as np
-from scipy.sparse.linalg import aslinearoperator
+
 
 from ...utils import dip_azimuth2cartesian, mkvc, sdiag, validate_string, validate_type
 from ..base import BaseEquivalentSourceLayerSimulation, BasePFSimulation
