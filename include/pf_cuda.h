@@ -332,7 +332,8 @@ int pf_probe_fp64_peak(double *flops, void *stream);
 
 /* Element-wise probe of the fp64 building blocks of the prism kernels (tests/test_gpu_math.py):
  * kind 0 = a / b, 1 = atan(a / b) (choclo _safe_atan2(a, b)), 2 = log(a / b) for a, b > 0,
- * 3 = choclo _safe_log(a, b, c, r) with r = sqrt(a^2 + b^2 + c^2).  `c` may be NULL for kinds 0-2. */
+ * 3 = choclo _safe_log(a, b, c, r) with r = sqrt(a^2 + b^2 + c^2), 4 = sqrt(a) for a == 0 or a normal
+ * double (bit-identical to the IEEE root).  `c` may be NULL for every kind but 3. */
 int pf_math_probe(int kind, const double *a, const double *b, const double *c, double *out, int64_t n,
                   void *stream);
 

@@ -139,7 +139,9 @@ template <int FAM>
 __device__ __forceinline__ void eval_raw(int need, double e, double n, double u, Raw10 &k)
 {
     // gravity/_numba/_3d_mesh.py:494-498: distance = sqrt(dx**2 + dy**2 + dz**2)
-    const double r = sqrt(e * e + n * n + u * u);
+    const double r2 = e * e + n * n + u * u;
+    const bool r_is_zero = r2 == 0.0;
+    const double r = pf_sqrt(r2, r_is_zero);
     if (FAM == 12) {
         double Aee = 0, Ann = 0, Auu = 0, Len = 0, Leu = 0, Lnu = 0;
         constexpr int NEED_ALL = NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU;
@@ -151,18 +153,18 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
         if (lockstep) {
             // all six primitives: two atans + three logs in lock-step (pf_math.cuh), third atan
             // from the identity below
-            pf_node_atan2_log3(e, n, u, r, Aee, Ann, Len, Leu, Lnu);
+            pf_node_atan2_log3(e, n, u, r, r_is_zero, Aee, Ann, Len, Leu, Lnu);
             need = NEED_AUU;
         }
         // one atan + the two logs of the same axis (bx / by / bz, gx / gy / gz): lock-step as well
         if (need == (NEED_AEE | NEED_LEN | NEED_LEU)) {
-            pf_node_atan1_log2(e, n, u, r, Aee, Len, Leu);
+            pf_node_atan1_log2(e, n, u, r, r_is_zero, Aee, Len, Leu);
             need = 0;
         } else if (need == (NEED_ANN | NEED_LEN | NEED_LNU)) {
-            pf_node_atan1_log2(n, u, e, r, Ann, Lnu, Len);
+            pf_node_atan1_log2(n, u, e, r, r_is_zero, Ann, Lnu, Len);
             need = 0;
         } else if (need == (NEED_AUU | NEED_LEU | NEED_LNU)) {
-            pf_node_atan1_log2(u, e, n, r, Auu, Leu, Lnu);
+            pf_node_atan1_log2(u, e, n, r, r_is_zero, Auu, Leu, Lnu);
             need = 0;
         }
         if (need & NEED_AEE) Aee = pf_safe_atan2(n * u, e * r);
@@ -289,9 +291,11 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         const double a = (axis == 0) ? e : ((axis == 1) ? n : u);
         const double b = (axis == 0) ? n : ((axis == 1) ? u : e);
         const double c = (axis == 0) ? u : ((axis == 1) ? e : n);
-        const double r = sqrt(e * e + n * n + u * u);
+        const double r2 = e * e + n * n + u * u;
+        const bool r_is_zero = r2 == 0.0;
+        const double r = pf_sqrt(r2, r_is_zero);
         double A, Lc, Lb;
-        pf_node_atan1_log2(a, b, c, r, A, Lc, Lb);
+        pf_node_atan1_log2(a, b, c, r, r_is_zero, A, Lc, Lb);
         planes[j] = -(b * Lc + c * Lb - a * A);
         return;
     }
@@ -515,6 +519,22 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
 #define PF_MARCH_MIN_BLOCKS 3
 #endif
 
+// shared-memory accesses through 32-bit shared-window addresses with compile-time offsets: the
+// cell phase forms one address per slot and everything else is an immediate (left to itself the
+// compiler re-derives the CTA's shared window and the buffer bases for every slot)
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f64(unsigned addr, double v)
+{
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v));
+}
+
 // sign of a node's atan sum S = Aee + Ann + Auu as an integer: +-1 for +-pi/2, 0 when two or
 // more coordinates vanish (the safe_atan2 conventions, see eval_raw)
 __device__ __forceinline__ int node_S_sign(double e, double n, double u)
@@ -550,6 +570,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     __shared__ int s_role[MAX_OUT];
 
     const int tid = threadIdx.x;
+    const unsigned smem32 = (unsigned)__cvta_generic_to_shared(smem);          // shared-window addresses
+    const unsigned dprev32 = (unsigned)__cvta_generic_to_shared(dprev) + tid * 8;
     const int nx = p.plan.grid_nx, ny = p.plan.grid_ny;
     const int32_t *fp = ((NR == 4) ? p.plan.footprints4 : p.plan.footprints2) + 6 * blockIdx.x;
     const int ix0 = fp[0], iy0 = fp[1], fw = fp[2], fh = fp[3];
@@ -757,29 +779,37 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 unsigned long long dst[NO];
 #pragma unroll
                 for (int o = 0; o < NO; ++o) dst[o] = s_dst[o];
+                const unsigned pl32 = smem32 + (unsigned)(pl - reinterpret_cast<const char *>(smem));
 #pragma unroll
                 for (int s = 0; s < NR; ++s) {
                     if (cbase[s] < 0) continue;
-                    const char *q = pl + o00[s];
-                    double *dp = dprev + tid + s * PF_THREADS;
+                    const unsigned q0 = pl32 + o00[s];       // node (x0, y0) of the cell, plane 0
+                    const unsigned q1 = q0 + sW;             // node (x0, y1)
                     const bool st = col[s] >= 0;
                     const unsigned cu = (unsigned)col[s];
-#pragma unroll
-                    for (int o = 0; o < NO; ++o) {
-                        const char *qq = q + o * LAYER_BYTES;
-                        const double d_new = *reinterpret_cast<const double *>(qq)
-                                             - *reinterpret_cast<const double *>(qq + 8)
-                                             - *reinterpret_cast<const double *>(qq + sW)
-                                             + *reinterpret_cast<const double *>(qq + sW + 8);
-                        const double d_old = dp[o * (NR * PF_THREADS)];
-                        dp[o * (NR * PF_THREADS)] = d_new;
-                        const double g = factor * (d_new - d_old);
-                        if (SINK == SINK_STORE) {
-                            if (st) reinterpret_cast<GT *>(dst[o])[cu] = (GT)g;
-                        } else {
-                            if (st) fsum += g * __ldg(reinterpret_cast<const double *>(dst[o]) + cu);
-                        }
+#define PF_FIXED_OUT(O)                                                                              \
+                    if (O < NO) {                                                                     \
+                        const double d_new = lds_f64<(O) * LAYER_BYTES>(q0) - lds_f64<(O) * LAYER_BYTES + 8>(q0) \
+                                             - lds_f64<(O) * LAYER_BYTES>(q1) + lds_f64<(O) * LAYER_BYTES + 8>(q1); \
+                        const double d_old = (s == 0)   ? lds_f64<((O) * NR + 0) * PF_THREADS * 8>(dprev32) \
+                                             : (s == 1) ? lds_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dprev32) \
+                                             : (s == 2) ? lds_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dprev32) \
+                                                        : lds_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dprev32); \
+                        if (s == 0) sts_f64<((O) * NR + 0) * PF_THREADS * 8>(dprev32, d_new);            \
+                        else if (s == 1) sts_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dprev32, d_new);  \
+                        else if (s == 2) sts_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dprev32, d_new);  \
+                        else sts_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dprev32, d_new);              \
+                        const double g = factor * (d_new - d_old);                                    \
+                        if (SINK == SINK_STORE) {                                                     \
+                            if (st) reinterpret_cast<GT *>(dst[(O) < NO ? (O) : 0])[cu] = (GT)g;      \
+                        } else {                                                                      \
+                            if (st) fsum += g * __ldg(reinterpret_cast<const double *>(dst[(O) < NO ? (O) : 0]) + cu); \
+                        }                                                                             \
                     }
+                    PF_FIXED_OUT(0)
+                    PF_FIXED_OUT(1)
+                    PF_FIXED_OUT(2)
+#undef PF_FIXED_OUT
                 }
                 if (SINK == SINK_FORWARD && emit) {
                     fsum = warp_sum(fsum);

@@ -643,7 +643,7 @@ extern "C" int pf_probe_fp64_peak(double *flops, void *stream_)
 // ---------------------------------------------------------------------------
 // Element-wise probe of the branch-free fp64 building blocks of pf_math.cuh (tests only):
 // kind 0 = pf_div(a, b), 1 = pf_atan_ratio(a, b) = atan(a / b), 2 = pf_log_ratio(a, b) = log(a / b),
-// 3 = pf_safe_log(a, b, c) with r = sqrt(a^2 + b^2 + c^2).
+// 3 = pf_safe_log(a, b, c) with r = sqrt(a^2 + b^2 + c^2), 4 = pf_sqrt(a).
 // ---------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(256) math_probe_kernel(int kind, const double *a, const double *b,
@@ -655,6 +655,7 @@ __global__ void __launch_bounds__(256) math_probe_kernel(int kind, const double 
     if (kind == 0) v = pf_div(a[i], b[i]);
     else if (kind == 1) v = pf_atan_ratio(a[i], b[i]);
     else if (kind == 2) v = pf_log_ratio(a[i], b[i]);
+    else if (kind == 4) v = pf_sqrt(a[i]);
     else v = pf_safe_log(a[i], b[i], c[i], sqrt(a[i] * a[i] + b[i] * b[i] + c[i] * c[i]));
     out[i] = v;
 }
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(256) math_probe_kernel(int kind, const double 
 extern "C" int pf_math_probe(int kind, const double *a, const double *b, const double *c, double *out,
                              int64_t n, void *stream)
 {
-    PF_CHECK_ARG(kind >= 0 && kind <= 3, "bad kind");
+    PF_CHECK_ARG(kind >= 0 && kind <= 4, "bad kind");
     PF_CHECK_ARG(n >= 0, "negative length");
     if (n == 0) return PF_OK;
     PF_CHECK_ARG(a && b && out && (kind != 3 || c), "null vector");

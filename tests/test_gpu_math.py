@@ -82,3 +82,16 @@ def test_log_ratio_and_safe_log():
     exact[1000] = -np.log(np.longdouble(14.0))       # on the axis: -log(-2x)
     exact[1001] = 0.0                                # r == 0
     assert np.all(np.abs(got - exact.astype(np.float64)) <= 4e-16 * np.maximum(1.0, np.abs(got)))
+
+
+def test_sqrt_is_the_ieee_root():
+    # pf_sqrt = the fast path of sqrt.rn.f64 without its range check: bit-identical to the correctly
+    # rounded root on squared distances (0 and normal doubles), which the `r == -x` axis test of
+    # _safe_log relies on
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    x = np.r_[rng.uniform(0.5, 2.0, n) * 10.0 ** rng.uniform(-12, 14, n), [0.0, 1.0, 4.0, 2.0, 1e-200, 1e200]]
+    e, nn, u = rng.uniform(-500, 500, (3, 100_000))
+    x = np.r_[x, e * e + nn * nn + u * u, (e * e)]      # exact squares: the axis case r == |e|
+    got = probe(4, x, x)
+    assert np.array_equal(got, np.sqrt(x))
