@@ -87,8 +87,11 @@ typedef struct {
      * (colmap == NULL: all cells active, column = index; -1 = inactive).
      * Footprints are given for two node capacities per layer: 1024 ("4") and
      * 512 ("2") nodes; each is (ix0, iy0, width, height, iz_begin, iz_end): an
-     * (x, y) rectangle of cells with (width + 1)(height + 1) <= capacity and the
-     * range of cell layers [iz_begin, iz_end) that holds its active cells.
+     * (x, y) rectangle of cells with (width + 1)(height + 1) <= capacity,
+     * width + 1 <= 256 (a thread of the 256-thread CTA keeps one node column; a
+     * wider footprint traps the kernel) and the range of cell layers
+     * [iz_begin, iz_end) that holds its active cells.  A footprint costs
+     * ceil((height + 1) / floor(256 / (width + 1))) node rounds per layer.
      */
     int32_t grid_nx, grid_ny, grid_nz;
     int32_t n_footprints4, n_footprints2;

@@ -544,10 +544,6 @@ __device__ __forceinline__ int node_S_sign(double e, double n, double u)
     return zeros >= 2 ? 0 : (sb ? -1 : 1);
 }
 
-#ifndef PF_UNROLL_NODES
-#define PF_UNROLL_NODES 0
-#endif
-
 template <int FAM, int PROG, int SINK, typename GT, int NR>
 __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     pf_march_kernel(const __grid_constant__ LaunchParams p)
@@ -587,15 +583,17 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const bool has_derived = !PF_FIXED(PROG) && n_out > n_plain;
 
     // ---- footprint-stationary state -------------------------------------------
-    double x[NR], y[NR];
-#pragma unroll
-    for (int k = 0; k < NR; ++k) {
-        const int j = tid + k * PF_THREADS;
-        const int ly = j / W1, lx = j - ly * W1;
-        const bool ok = j < n_layer_nodes;
-        x[k] = ok ? p.plan.grid_xs[ix0 + lx] : 0.0;
-        y[k] = ok ? p.plan.grid_ys[iy0 + ly] : 0.0;
-    }
+    // Node phase: the layer's nodes are taken R = THREADS / W1 whole rows at a time, so thread tid
+    // owns node column lx = tid % W1 in rows tid / W1 + R k -- plane index tid + k R W1, the same
+    // x for every node of the thread (e = x - rx is formed once per receiver and its square hoisted
+    // out of the layer loop; the y of a round is one L1 load).  Footprints wider than THREADS - 1
+    // cells are a plan error (include/pf_cuda.h; tiling.march_footprints never makes them).
+    if (W1 > PF_THREADS) __trap();
+    const int RW = (PF_THREADS / W1) * W1;            // node slots per round
+    const int rows_per_round = PF_THREADS / W1;
+    const bool node_thread = tid < RW;
+    const double xnode = __ldg(p.plan.grid_xs + ix0 + (node_thread ? tid % W1 : 0));
+    const double *yrow = p.plan.grid_ys + iy0 + (node_thread ? tid / W1 : 0);
     const int n_layer_cells = fw * fh;
     int o00[NR];       // byte offset of the cell's (x0, y0) node inside a layer plane
     int cbase[NR];     // mesh index of the cell in layer 0, -1 = no cell in this slot
@@ -637,23 +635,15 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
         const bool rx_in_box = has_derived && rx >= box_x0 && rx <= box_x1 && ry >= box_y0 && ry <= box_y1;
 
         // ---- phase 1: output planes of node layer L -> planes ---------------------------
+        const double e = xnode - rx;
         auto phase1 = [&](int L, double *planes) {
             const double u = __ldg(p.plan.grid_zs + L) - rz;
-#if PF_UNROLL_NODES
-#pragma unroll
-            for (int k = 0; k < NR; ++k) {
-                const int j = tid + k * PF_THREADS;
-                if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, x[k] - rx, y[k] - ry, u, planes, j);
-            }
-#else
+            if (node_thread) {
+                const double *yp = yrow;
 #pragma unroll 1
-            for (int k = 0; k < NR; ++k) {
-                const int j = tid + k * PF_THREADS;
-                const double xx = (k == 0) ? x[0] : ((k == 1) ? x[1 % NR] : ((k == 2) ? x[2 % NR] : x[3 % NR]));
-                const double yy = (k == 0) ? y[0] : ((k == 1) ? y[1 % NR] : ((k == 2) ? y[2 % NR] : y[3 % NR]));
-                if (j < n_layer_nodes) eval_node<FAM, PROG, NCAP>(p, xx - rx, yy - ry, u, planes, j);
+                for (int j = tid; j < n_layer_nodes; j += RW, yp += rows_per_round)
+                    eval_node<FAM, PROG, NCAP>(p, e, __ldg(yp) - ry, u, planes, j);
             }
-#endif
         };
         // exact sum_v s_v S_v of the cell in slot s between node layers L-1 and L (rare path)
         auto cell_S = [&](int s, int L) -> double {

@@ -295,8 +295,8 @@ def build_tile_plan_tensor(axis_nodes, active_index=None, with_tiles=True) -> Ti
     # keep a footprint set only if it evaluates fewer node slots per cell than the bricks
     for name, ncap in (("footprints4", 1024), ("footprints2", 512)):
         fps = march_footprints(nx, ny, nz, ncap, act)
-        nodes = (fps[:, 2].astype(np.int64) + 1) * (fps[:, 3] + 1)
-        slots = float(((-(-nodes // _ROUND) * _ROUND) * (fps[:, 5] - fps[:, 4] + 1)).sum())
+        rounds = march_node_rounds(fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64))
+        slots = float(((rounds * _ROUND) * (fps[:, 5] - fps[:, 4] + 1)).sum())
         setattr(plan, name, fps if slots < 0.95 * brick_slots else np.zeros((0, 6), np.int32))
     if with_tiles:
         plan.ensure_tiles()
@@ -308,12 +308,22 @@ def _axis_parts(d, b):
     return [(b, full)] + ([(rem, 1)] if rem else [])
 
 
+def march_node_rounds(w, h):
+    """256-thread node rounds per layer of a w x h-cell footprint (whole node rows per round)."""
+    rows = np.maximum(_ROUND // (np.asarray(w) + 1), 1)
+    return -(-(np.asarray(h) + 1) // rows)
+
+
 def march_footprints(nx, ny, nz, ncap, active_index=None):
     """
     (x, y) footprints for the z-marching kernel: an a x b grid of rectangles,
-    each with (w + 1)(h + 1) <= ncap nodes per layer, chosen to minimise the
-    number of 256-thread node rounds per layer; rows are
+    each with (w + 1)(h + 1) <= ncap nodes per layer and w + 1 <= 256, chosen to
+    minimise the number of 256-thread node rounds per layer; rows are
     (ix0, iy0, w, h, iz_begin, iz_end).
+
+    The kernel takes a layer's nodes floor(256 / (w + 1)) whole rows per round
+    (a thread keeps one node column, csrc/pf_build.cu), so a footprint costs
+    ceil((h + 1) / floor(256 / (w + 1))) node rounds.
     """
     # every (a, b) split (this runs inside every simulation's first G access): one numpy pass over
     # the whole (a, b) table for ordinary meshes, row blocks of it for huge ones (bounded memory)
@@ -325,8 +335,9 @@ def march_footprints(nx, ny, nz, ncap, active_index=None):
         a_blk = np.arange(a0, min(a0 + rows_per_block, nx + 1), dtype=np.int64)[:, None]
         w_blk = -(-nx // a_blk)
         nodes_all = (w_blk + 1) * (h_all + 1)
-        cost = (a_blk * b_all * (4 * -(-nodes_all // _ROUND) + -(-(w_blk * h_all) // _ROUND))).astype(np.float64)
-        cost[(nodes_all > ncap) | ((w_blk + 1) * 2 > ncap)] = np.inf
+        rounds_all = march_node_rounds(w_blk, h_all)
+        cost = (a_blk * b_all * (4 * rounds_all + -(-(w_blk * h_all) // _ROUND))).astype(np.float64)
+        cost[(nodes_all > ncap) | ((w_blk + 1) * 2 > ncap) | (w_blk + 1 > _ROUND)] = np.inf
         flat = int(np.argmin(cost))            # row-major: smallest a, then smallest b, among equals
         c = float(cost.flat[flat])
         if np.isfinite(c) and (best is None or c < best[0]):

@@ -12,7 +12,7 @@ from helpers import RTOL_NORMWISE, rowwise_rel, vec_rel
 from oracle.oracle import OracleSimulation
 from simpeg_b200.engine import CudaEngine
 from simpeg_b200.meshes import TensorMesh, synthetic_octree
-from simpeg_b200.tiling import build_tile_plan_tensor, tensor_axes_of
+from simpeg_b200.tiling import build_tile_plan_tensor, march_footprints, tensor_axes_of
 
 pytestmark = pytest.mark.gpu
 
@@ -161,6 +161,44 @@ def test_marching_kernel_vs_tile_kernel_and_oracle(physics, comps, mt, masked):
     m32 = CudaEngine(physics, None, None, [(loc, comps)], sensitivity_dtype=np.float32, **kw)
     m32.build_G()
     assert rowwise_rel(m32.G_to_numpy(), G_ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("shape", [(151, 7, 3), (3, 60, 4), (255, 2, 2), (300, 5, 2), (64, 64, 3), (1, 1, 5), (37, 23, 6)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_marching_kernel_footprint_shapes(shape):
+    """Node phase of the z-marching kernel on footprints of every aspect ratio: one node row per
+    round (151 or 255 nodes wide), 64 rows per round (4 nodes wide), full-width meshes that need
+    several footprints, non-uniform spacing, a single cell column.  G rows, forward and the
+    blocked diagonal against the oracle; TMI vector (3 planes, 1024-node footprints) and the
+    seven-component gravity set (6 planes, 512-node footprints, derived gzz)."""
+    rng = np.random.default_rng(21)
+    hx, hy, hz = (rng.uniform(2.0, 5.0, n) for n in shape)
+    mesh = TensorMesh([hx, hy, hz], "CCN")
+    # receivers over the mesh (far outside it the reference's own rounding exceeds the bar, see
+    # test_altitude_parity.py)
+    # ... and off its symmetry planes (rows that vanish by symmetry have no row-wise scale)
+    loc = grid_receivers(6, 1.0, 1.5, 4)
+    loc[:, :2] += rng.uniform(-0.3, 0.3, (6, 2))
+    loc[:, 0] *= 0.4 * hx.sum()
+    loc[:, 1] *= 0.4 * hy.sum()
+    loc[0] = [mesh.nodes_x[shape[0] // 2], mesh.nodes_y[shape[1] // 2], 0.0]    # on a surface node
+    plan = build_tile_plan_tensor(tensor_axes_of(mesh))
+    # the planner drops footprint sets that are no better than bricks on such meshes: force them
+    plan.footprints4 = march_footprints(*shape, 1024)
+    plan.footprints2 = march_footprints(*shape, 512)
+    for physics, comps, mt in (("magnetics", ["tmi"], "vector"),
+                               ("gravity", ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"], "scalar")):
+        eng = CudaEngine(physics, None, None, [(loc, comps)], b0=B0, model_type=mt, plan=plan, use_marching=True)
+        assert eng.plan.grid_nx == shape[0] and "pf_march_kernel" in eng.describe("store")
+        ora = OracleSimulation(physics, mesh.nodes, mesh.cell_nodes, [(loc, comps)], b0=B0, model_type=mt)
+        G_ref = ora.sensitivity_matrix()
+        eng.build_G()
+        assert rowwise_rel(eng.G_to_numpy(), G_ref).max() <= RTOL_NORMWISE
+        m = rng.uniform(-0.5, 0.5, eng.nP)
+        assert vec_rel(eng.to_host(eng.forward_dev(eng.to_device(m))), G_ref @ m) <= RTOL_NORMWISE
+        w = rng.uniform(0.5, 1.5, eng.n_rows)
+        assert vec_rel(eng.to_host(eng.gtg_diag_dev(eng.to_device(w))),
+                       np.einsum("i,ij,ij->j", w, G_ref, G_ref)) <= RTOL_NORMWISE
 
 
 def test_row_blocks_are_independent():

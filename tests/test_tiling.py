@@ -106,3 +106,24 @@ def test_empty_and_invalid():
         build_tile_plan(np.zeros((4, 2)), np.zeros((1, 8), dtype=np.int64))
     with pytest.raises(ValueError):
         build_tile_plan(np.zeros((4, 3)), np.full((1, 8), 7, dtype=np.int64))
+
+
+@pytest.mark.parametrize("shape", [(100, 100, 10), (40, 40, 20), (200, 200, 4), (600, 3, 2), (3, 600, 2),
+                                   (151, 7, 3), (255, 2, 1), (256, 1, 1), (1, 1, 1), (130, 97, 5)])
+def test_march_footprints_cover_the_mesh_within_the_kernel_limits(shape):
+    """Footprints of the z-marching kernel: every (x, y) cell column exactly once, node capacity
+    per layer respected, and no footprint wider than the CTA (one node column per thread)."""
+    from simpeg_b200.tiling import march_footprints, march_node_rounds
+
+    nx, ny, nz = shape
+    for ncap in (1024, 512):
+        fps = march_footprints(nx, ny, nz, ncap)
+        cover = np.zeros((nx, ny), dtype=int)
+        for ix0, iy0, w, h, z0, z1 in fps:
+            assert (w + 1) * (h + 1) <= ncap and w + 1 <= 256 and w >= 1 - (nx == 1) and h >= 1 - (ny == 1)
+            assert (z0, z1) == (0, nz)
+            cover[ix0:ix0 + w, iy0:iy0 + h] += 1
+        assert (cover == 1).all()
+        # the node-round count the planner minimises is the kernel's: whole rows per round
+        w, h = fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64)
+        assert np.array_equal(march_node_rounds(w, h), -(-(h + 1) // (256 // (w + 1))))
