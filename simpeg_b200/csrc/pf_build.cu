@@ -769,7 +769,11 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 unsigned long long dst[NO];
 #pragma unroll
                 for (int o = 0; o < NO; ++o) dst[o] = s_dst[o];
-                const unsigned pl32 = smem32 + (unsigned)(pl - reinterpret_cast<const char *>(smem));
+                // formed once per layer and made opaque: the compiler otherwise rematerialises both
+                // bases (shared window, buffer parity, thread index) in front of every slot
+                unsigned pl32 = smem32 + (unsigned)(pl - reinterpret_cast<const char *>(smem));
+                unsigned dp32 = dprev32;
+                asm volatile("" : "+r"(pl32), "+r"(dp32));
 #pragma unroll
                 for (int s = 0; s < NR; ++s) {
                     if (cbase[s] < 0) continue;
@@ -781,14 +785,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                     if (O < NO) {                                                                     \
                         const double d_new = lds_f64<(O) * LAYER_BYTES>(q0) - lds_f64<(O) * LAYER_BYTES + 8>(q0) \
                                              - lds_f64<(O) * LAYER_BYTES>(q1) + lds_f64<(O) * LAYER_BYTES + 8>(q1); \
-                        const double d_old = (s == 0)   ? lds_f64<((O) * NR + 0) * PF_THREADS * 8>(dprev32) \
-                                             : (s == 1) ? lds_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dprev32) \
-                                             : (s == 2) ? lds_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dprev32) \
-                                                        : lds_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dprev32); \
-                        if (s == 0) sts_f64<((O) * NR + 0) * PF_THREADS * 8>(dprev32, d_new);            \
-                        else if (s == 1) sts_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dprev32, d_new);  \
-                        else if (s == 2) sts_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dprev32, d_new);  \
-                        else sts_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dprev32, d_new);              \
+                        const double d_old = (s == 0)   ? lds_f64<((O) * NR + 0) * PF_THREADS * 8>(dp32) \
+                                             : (s == 1) ? lds_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dp32) \
+                                             : (s == 2) ? lds_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dp32) \
+                                                        : lds_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dp32); \
+                        if (s == 0) sts_f64<((O) * NR + 0) * PF_THREADS * 8>(dp32, d_new);            \
+                        else if (s == 1) sts_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dp32, d_new);  \
+                        else if (s == 2) sts_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dp32, d_new);  \
+                        else sts_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dp32, d_new);              \
                         const double g = factor * (d_new - d_old);                                    \
                         if (SINK == SINK_STORE) {                                                     \
                             if (st) reinterpret_cast<GT *>(dst[(O) < NO ? (O) : 0])[cu] = (GT)g;      \
