@@ -104,6 +104,7 @@ struct LaunchParams {
     PlaneDesc planes[MAX_PLANES];
     OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
+    double gx, gy, gz;  // TMI programs: factor x unit inducing field (the outputs' factors are 1)
     // sinks
     void *G;
     int64_t ldG;
@@ -270,15 +271,19 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         // one component "tmi" (magnetics/_numba/_3d_mesh.py:352-372), hoisted to the node
         eval_raw<12>(NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU, e, n, u, k);
         // (explicit FMAs: this combination is hoisted to the node anyway, see the header)
-        const double bx = fma(k.v4, fz, fma(k.v3, fy, k.v0 * fx));
-        const double by = fma(k.v5, fz, fma(k.v1, fy, k.v3 * fx));
-        const double bz = fma(k.v2, fz, fma(k.v5, fy, k.v4 * fx));
+        // the unit factor cf |B0| of the component rides on the (last) contraction with the field
+        // direction -- g = factor f, formed on the host -- instead of one multiplication per cell
+        // and output
+        const double gx = p.gx, gy = p.gy, gz = p.gz;
         if (PROG == PROG_TMI_SCALAR) {
-            planes[j] = fma(bz, fz, fma(by, fy, bx * fx));
+            const double bx = fma(k.v4, fz, fma(k.v3, fy, k.v0 * fx));
+            const double by = fma(k.v5, fz, fma(k.v1, fy, k.v3 * fx));
+            const double bz = fma(k.v2, fz, fma(k.v5, fy, k.v4 * fx));
+            planes[j] = fma(bz, gz, fma(by, gy, bx * gx));
         } else {
-            planes[j] = bx;
-            planes[STRIDE + j] = by;
-            planes[2 * STRIDE + j] = bz;
+            planes[j] = fma(k.v4, gz, fma(k.v3, gy, k.v0 * gx));
+            planes[STRIDE + j] = fma(k.v5, gz, fma(k.v1, gy, k.v3 * gx));
+            planes[2 * STRIDE + j] = fma(k.v2, gz, fma(k.v5, gy, k.v4 * gx));
         }
         return;
     }
@@ -793,7 +798,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                         else if (s == 1) sts_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dp32, d_new);  \
                         else if (s == 2) sts_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dp32, d_new);  \
                         else sts_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dp32, d_new);              \
-                        const double g = factor * (d_new - d_old);                                    \
+                        const double g = PF_IS_TMI(PROG) ? (d_new - d_old) : factor * (d_new - d_old); \
                         if (SINK == SINK_STORE) {                                                     \
                             if (st) reinterpret_cast<GT *>(dst[(O) < NO ? (O) : 0])[cu] = (GT)g;      \
                         } else {                                                                      \
@@ -1362,7 +1367,15 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
             bool regular = p.direct && p.n_out == p.nblk;
             for (int o = 0; o < p.n_out && regular; ++o)
                 regular = p.outs[o].blk == o && p.outs[o].factor == p.outs[0].factor;
-            if (regular) passes[i].prog = (p.nblk == 3) ? PROG_TMI_VECTOR : PROG_TMI_SCALAR;
+            if (regular) {
+                passes[i].prog = (p.nblk == 3) ? PROG_TMI_VECTOR : PROG_TMI_SCALAR;
+                // the common factor moves into the node evaluation (eval_node)
+                const double factor = p.outs[0].factor;
+                p.gx = factor * p.fx;
+                p.gy = factor * p.fy;
+                p.gz = factor * p.fz;
+                for (int o = 0; o < p.n_out; ++o) p.outs[o].factor = 1.0;
+            }
         }
         else if (passes[i].family == 12 &&
                  p.need == (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU))
