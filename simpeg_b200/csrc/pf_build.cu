@@ -105,6 +105,7 @@ struct LaunchParams {
     OutDesc outs[MAX_OUT];
     double fx, fy, fz;  // unit inducing field
     double gx, gy, gz;  // TMI programs: factor x unit inducing field (the outputs' factors are 1)
+    double f2x, f2y, f2z, g2x, g2y, g2z;  // 2 f and 2 g: coefficients of the halved logarithms
     // sinks
     void *G;
     int64_t ldG;
@@ -136,7 +137,8 @@ __device__ __forceinline__ double kernel_iij(double xi, double xj, double xk, do
 }
 
 // Node kernels of one (receiver, node) pair.
-template <int FAM>
+// HALF_LOGS (TMI programs, all six primitives): k.v3 .. k.v5 hold log / 2 (pf_math.cuh)
+template <int FAM, bool HALF_LOGS = false>
 __device__ __forceinline__ void eval_raw(int need, double e, double n, double u, Raw10 &k)
 {
     // gravity/_numba/_3d_mesh.py:494-498: distance = sqrt(dx**2 + dy**2 + dz**2)
@@ -154,7 +156,7 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
         if (lockstep) {
             // all six primitives: two atans + three logs in lock-step (pf_math.cuh), third atan
             // from the identity below
-            pf_node_atan2_log3(e, n, u, r, r_is_zero, Aee, Ann, Len, Leu, Lnu);
+            pf_node_atan2_log3<HALF_LOGS>(e, n, u, r, r_is_zero, Aee, Ann, Len, Leu, Lnu);
             need = NEED_AUU;
         }
         // one atan + the two logs of the same axis (bx / by / bz, gx / gy / gz): lock-step as well
@@ -189,6 +191,7 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
         if (need & NEED_LEN) Len = pf_safe_log(u, e, n, r);
         if (need & NEED_LEU) Leu = pf_safe_log(n, e, u, r);
         if (need & NEED_LNU) Lnu = pf_safe_log(e, n, u, r);
+        if (HALF_LOGS && !lockstep) { Len *= 0.5; Leu *= 0.5; Lnu *= 0.5; }   // (ablation builds only)
         k.v0 = -Aee;  // kernel_ee
         k.v1 = -Ann;  // kernel_nn
         k.v2 = -Auu;  // kernel_uu
@@ -269,21 +272,21 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
     const double fx = p.fx, fy = p.fy, fz = p.fz;
     if (PF_IS_TMI(PROG)) {
         // one component "tmi" (magnetics/_numba/_3d_mesh.py:352-372), hoisted to the node
-        eval_raw<12>(NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU, e, n, u, k);
+        // the three logarithms arrive halved (HALF_LOGS) and meet doubled field coefficients (exact)
+        eval_raw<12, true>(NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU, e, n, u, k);
         // (explicit FMAs: this combination is hoisted to the node anyway, see the header)
         // the unit factor cf |B0| of the component rides on the (last) contraction with the field
         // direction -- g = factor f, formed on the host -- instead of one multiplication per cell
         // and output
-        const double gx = p.gx, gy = p.gy, gz = p.gz;
         if (PROG == PROG_TMI_SCALAR) {
-            const double bx = fma(k.v4, fz, fma(k.v3, fy, k.v0 * fx));
-            const double by = fma(k.v5, fz, fma(k.v1, fy, k.v3 * fx));
-            const double bz = fma(k.v2, fz, fma(k.v5, fy, k.v4 * fx));
-            planes[j] = fma(bz, gz, fma(by, gy, bx * gx));
+            const double bx = fma(k.v4, p.f2z, fma(k.v3, p.f2y, k.v0 * fx));
+            const double by = fma(k.v5, p.f2z, fma(k.v1, fy, k.v3 * p.f2x));
+            const double bz = fma(k.v2, fz, fma(k.v5, p.f2y, k.v4 * p.f2x));
+            planes[j] = fma(bz, p.gz, fma(by, p.gy, bx * p.gx));
         } else {
-            planes[j] = fma(k.v4, gz, fma(k.v3, gy, k.v0 * gx));
-            planes[STRIDE + j] = fma(k.v5, gz, fma(k.v1, gy, k.v3 * gx));
-            planes[2 * STRIDE + j] = fma(k.v2, gz, fma(k.v5, gy, k.v4 * gx));
+            planes[j] = fma(k.v4, p.g2z, fma(k.v3, p.g2y, k.v0 * p.gx));
+            planes[STRIDE + j] = fma(k.v5, p.g2z, fma(k.v1, p.gy, k.v3 * p.g2x));
+            planes[2 * STRIDE + j] = fma(k.v2, p.gz, fma(k.v5, p.g2y, k.v4 * p.g2x));
         }
         return;
     }
@@ -1375,6 +1378,8 @@ int make_passes(const pf_plan *plan, const pf_job *job, Pass *passes, int max_pa
                 p.gy = factor * p.fy;
                 p.gz = factor * p.fz;
                 for (int o = 0; o < p.n_out; ++o) p.outs[o].factor = 1.0;
+                p.f2x = 2.0 * p.fx; p.f2y = 2.0 * p.fy; p.f2z = 2.0 * p.fz;
+                p.g2x = 2.0 * p.gx; p.g2y = 2.0 * p.gy; p.g2z = 2.0 * p.gz;
             }
         }
         else if (passes[i].family == 12 &&
