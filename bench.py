@@ -347,20 +347,29 @@ def stored_g_parity(wl, sim, coll, b0, n_sample, torch, dist):
 
 
 # --------------------------------------------------------------------------- measured DRAM traffic
+TRAFFIC_TABLES = ("r2z_traffic.json", "r2_traffic.json")   # newest capture of the round first
+
+
 def measured_traffic(kernel_name, algorithmic_bytes):
     """DRAM bytes per launch of the dominant kernel from THIS round's committed ncu capture
-    (profiles/r2_traffic.json, written by scripts/ncu_traffic.py from `ncu --set full`), scaled by
-    the algorithmic bytes of this run; None when the capture does not cover the kernel."""
-    try:
-        table = json.load(open(ROOT / "profiles" / "r2_traffic.json"))
-    except (OSError, ValueError):
+    (profiles/r2z_traffic.json -- the final kernels of the round -- else r2_traffic.json, written by
+    scripts/ncu_traffic.py from `ncu --set full`), scaled by the algorithmic bytes of this run; None
+    when the capture does not cover the kernel."""
+    table = None
+    for name in TRAFFIC_TABLES:
+        try:
+            table = json.load(open(ROOT / "profiles" / name))
+            break
+        except (OSError, ValueError):
+            continue
+    if table is None:
         return None, "no ncu capture committed for this round"
     for entry in table.get("kernels", []):
         if entry["match"] in kernel_name:
             ratio = entry["dram_bytes"] / entry["algorithmic_bytes"]
             return ratio * algorithmic_bytes, (f"dram__bytes_read+write = {ratio:.4f} x algorithmic bytes in "
                                                f"{entry['source']}")
-    return None, "kernel not in profiles/r2_traffic.json"
+    return None, f"kernel not in profiles/{name}"
 
 
 def dev_ms(torch, fn, reps=3):

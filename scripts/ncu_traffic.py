@@ -3,7 +3,7 @@
 Turn `ncu --set full` captures (.ncu-rep, read here with `ncu -i ... --page raw --csv`) into the
 table bench.py reads for `roofline.traffic`: profiles/r2_traffic.json.
 
-    python scripts/ncu_traffic.py gpurun_out/prof_r2_build.ncu-rep gpurun_out/prof_r2_products.ncu-rep
+    python scripts/ncu_traffic.py [--tag r2z] 7.2e9 gpurun_out/prof_r2_build.ncu-rep gpurun_out/prof_r2_products.ncu-rep
 
 Per kernel: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) and the
 algorithmic bytes of that launch (G bytes the launch writes or reads: rows x cols x 8, from the
@@ -46,9 +46,14 @@ def read(rep):
 
 
 def main():
-    algorithmic = float(sys.argv[1])            # bytes of G one captured launch touches
-    table, md = {"kernels": []}, ["# ncu --set full, round 2 (one launch each; cold cache, profiler clocks)\n"]
-    for rep in sys.argv[2:]:
+    args = list(sys.argv[1:])
+    tag = "r2"
+    if args[0] == "--tag":                      # profiles/<tag>_traffic.json, <tag>_kernels_summary.md
+        tag = args[1]
+        args = args[2:]
+    algorithmic = float(args[0])                # bytes of G one captured launch touches
+    table, md = {"kernels": []}, [f"# ncu --set full, {tag} (one launch each; cold cache, profiler clocks)\n"]
+    for rep in args[1:]:
         for d in read(rep):
             name = d["Kernel Name"][0]
             rd = to_bytes(*d["dram__bytes_read.sum"])
@@ -57,7 +62,7 @@ def main():
                     ("column_kernel" if "column" in name else name.split("(")[0].split("::")[-1]))
             table["kernels"].append({"match": short, "kernel": name, "dram_bytes": rd + wr, "dram_read": rd,
                                      "dram_write": wr, "algorithmic_bytes": algorithmic,
-                                     "source": f"profiles/r2_kernels_summary.md (ncu --set full, {Path(rep).name})"})
+                                     "source": f"profiles/{tag}_kernels_summary.md (ncu --set full, {Path(rep).name})"})
             md.append(f"\n## {name}\n\n| metric | value | unit |\n|---|---|---|")
             for k in WANT:
                 if k in d:
@@ -65,8 +70,8 @@ def main():
             for k in sorted(d):
                 if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and float(d[k][0] or 0) >= 0.05:
                     md.append(f"| `{k}` | {d[k][0]} | {d[k][1]} |")
-    (ROOT / "profiles" / "r2_traffic.json").write_text(json.dumps(table, indent=1) + "\n")
-    (ROOT / "profiles" / "r2_kernels_summary.md").write_text("\n".join(md) + "\n")
+    (ROOT / "profiles" / f"{tag}_traffic.json").write_text(json.dumps(table, indent=1) + "\n")
+    (ROOT / "profiles" / f"{tag}_kernels_summary.md").write_text("\n".join(md) + "\n")
     print(json.dumps(table, indent=1))
 
 
