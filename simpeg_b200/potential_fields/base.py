@@ -24,6 +24,7 @@ import numpy as np
 import scipy.sparse as sp
 from scipy.sparse.linalg import LinearOperator, aslinearoperator
 
+from .. import zarr_store
 from ..utils import validate_active_indices, validate_string
 
 ENGINES = ("geoana", "choclo", "cuda")
@@ -528,10 +529,22 @@ class BasePFSimulation:
         return G
 
     def _write_sensitivities(self):
-        """Every rank writes its rows into the one file (rank 0 creates it)."""
+        """Every rank writes its rows into the one file (rank 0 creates it).  A ``sensitivity_path``
+        that ends in ``.zarr`` selects an uncompressed zarr (format 2) directory store in row chunks
+        -- what the reference's dask path keeps (``simpeg/dask/potential_fields/base.py:46-66``) and
+        ``dask.array.from_zarr`` reads back -- instead of the raw memmap of
+        gravity/simulation.py:599-606."""
         ops = self._ops
         coll, rows = ops.coll, ops.sharding.local_rows
         shape = (self.survey.nD, self._n_columns())
+        if zarr_store.wants_zarr(self.sensitivity_path):
+            writer = zarr_store.ZarrMatrixWriter(self.sensitivity_path, shape, self.sensitivity_dtype,
+                                                 create=coll.rank == 0)
+            coll.barrier()
+            for a, b, block in ops.engine.G_row_chunks():
+                writer.write_rows(rows[a:b], block)
+            coll.barrier()
+            return
         if coll.rank == 0:
             np.memmap(self.sensitivity_path, shape=shape, dtype=self.sensitivity_dtype, order="C",
                       mode="w+").flush()
@@ -547,12 +560,20 @@ class BasePFSimulation:
     def load_sensitivities(self, path=None):
         """
         Use a sensitivity matrix that is already on disk -- written by this engine or by the
-        reference with ``store_sensitivities="disk"`` (gravity/simulation.py:599-606, same raw
-        layout) -- instead of evaluating it: every rank uploads its rows to HBM.
+        reference with ``store_sensitivities="disk"`` -- instead of evaluating it: every rank uploads
+        its rows to HBM.  ``path`` is the raw row-major memmap of gravity/simulation.py:599-606, a
+        zarr (format 2) store, or a directory that holds ``sensitivity.zarr`` (the dask path's
+        layout, ``simpeg/dask/potential_fields/base.py:46-48``).
         """
         path = self.sensitivity_path if path is None else path
         shape = (self.survey.nD, self._n_columns())
-        source = np.memmap(path, shape=shape, dtype=self.sensitivity_dtype, order="C", mode="r")
+        nested = os.path.join(str(path), "sensitivity.zarr")
+        if zarr_store.is_zarr_store(path) or zarr_store.is_zarr_store(nested):
+            source = zarr_store.ZarrMatrixReader(path if zarr_store.is_zarr_store(path) else nested)
+            if source.shape != shape:
+                raise ValueError(f"zarr store holds a {source.shape} array, the simulation needs {shape}")
+        else:
+            source = np.memmap(path, shape=shape, dtype=self.sensitivity_dtype, order="C", mode="r")
         ops = self._ops
         ops.engine.load_G_rows(source, ops.sharding.local_rows)
         del source

@@ -159,6 +159,41 @@ def test_store_sensitivities_disk_roundtrip(tmp_path):
     assert vec_rel(sim3.dpred(rho), G @ rho) <= 1e-6
 
 
+def test_store_sensitivities_disk_zarr_roundtrip(tmp_path):
+    """A sensitivity_path that ends in .zarr: the matrix goes to an uncompressed zarr (format 2)
+    directory store in row chunks, the container of the reference's dask path
+    (simpeg/dask/potential_fields/base.py:46-66); load_sensitivities() takes the store itself, or
+    the directory that holds `sensitivity.zarr`, and uploads the rows instead of evaluating them."""
+    import json
+
+    from sim_fixtures import gravity_survey, small_mesh
+    from simpeg_b200 import maps
+    from simpeg_b200.potential_fields import gravity
+    from simpeg_b200.zarr_store import ZarrMatrixReader
+
+    mesh = small_mesh()
+    store = tmp_path / "sensitivity.zarr"
+    kw = dict(survey=gravity_survey(["gz", "gxx"]), rhoMap=maps.IdentityMap(nP=mesh.n_cells),
+              sensitivity_dtype=np.float32, sensitivity_path=str(store))
+    sim = gravity.Simulation3DIntegral(mesh, store_sensitivities="disk", **kw)
+    rho = np.random.default_rng(0).uniform(-0.5, 0.5, mesh.n_cells)
+    d = sim.dpred(rho)
+    G = sim.G.to_numpy()
+    meta = json.load(open(store / ".zarray"))
+    assert meta["shape"] == list(G.shape) and meta["compressor"] is None and meta["dtype"] == "<f4"
+    assert np.array_equal(ZarrMatrixReader(store).read_rows(np.arange(G.shape[0])), G.astype(np.float32))
+    for path in (str(store), str(tmp_path)):          # the store, or the dask path's directory around it
+        sim2 = gravity.Simulation3DIntegral(mesh, store_sensitivities="ram", **dict(kw, sensitivity_path=path))
+        sim2._sensitivity_matrix = None               # calling it would raise
+        sim2.load_sensitivities()
+        assert np.array_equal(sim2.dpred(rho), d)
+    # a store of another shape is refused
+    other = gravity.Simulation3DIntegral(mesh, store_sensitivities="ram",
+                                         **dict(kw, survey=gravity_survey(["gz"])))
+    with pytest.raises(ValueError, match="zarr store holds"):
+        other.load_sensitivities()
+
+
 @pytest.mark.parametrize("components", [["gxx", "gyy", "gzz"], ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"]],
                          ids=["trace", "cfg2-set"])
 def test_derived_gzz_with_receivers_touching_cells(components):
