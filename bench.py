@@ -99,7 +99,11 @@ def make_simulation(wl, survey, comm=None):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 100` on this rank's GPU.  Started BEFORE the warm-up steps (on an 8-GPU box
+    nvidia-smi needs longer to come up than the timed region lasts); `stop(window)` keeps the
+    samples whose timestamps fall inside the timed region and, when the region was too short to
+    catch any, the samples of warm-up + timed region (the same steps) -- `window` says which."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -119,7 +123,9 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -127,29 +133,32 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
+        rows = []
         for line in open(self.path):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                power.append(float(parts[3]))
+                stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((stamp, float(parts[1]), float(parts[2]), float(parts[3]),
+                             [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                 "sw_power_cap"), parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.path)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        used, which = rows, "whole run"
+        if window is not None:
+            inside = [r for r in rows if window[0] <= r[0] <= window[1]]
+            used, which = (inside, "timed region") if inside else (rows, "warm-up + timed region")
+        sm, mx, power = [r[1] for r in used], [r[2] for r in used], [r[3] for r in used]
+        reasons = sorted({n for r in used for n in r[4]})
         # "under load" = samples drawing more than half of the peak power seen
         pmax = max(power)
         loaded = [s for s, p in zip(sm, power) if p >= 0.5 * pmax] or sm
-        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": pmax}
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": reasons,
+                "samples": len(sm), "power_w_max": pmax, "window": which}
 
 
 # --------------------------------------------------------------------------- CPU baseline
@@ -665,12 +674,15 @@ def run_cuda(args):
             timers.append(ev)
         return full, z
 
+    import datetime
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     fp64_peak = probe_fp64_peak()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    t_region0 = datetime.datetime.now()
     launches0 = launch_count()
     timers = []
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -680,7 +692,7 @@ def run_cuda(args):
     e_stop.record()
     barrier()
     launches = launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop((t_region0, datetime.datetime.now()))
     K = args.steps
 
     def part(i, j):
