@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 5
+#define PF_ABI_VERSION 6
 
 typedef enum {
     PF_OK = 0,
@@ -92,10 +92,14 @@ typedef struct {
      * wider footprint traps the kernel) and the range of cell layers
      * [iz_begin, iz_end) that holds its active cells.  A footprint costs
      * ceil((height + 1) / floor(256 / (width + 1))) node rounds per layer.
+     * footprints4h (optional, n_footprints4h == 0: absent) is a set for the
+     * 128-thread variant of the kernel, which the three-plane programs prefer
+     * (twice as many, smaller CTAs per SM): (width + 1)(height + 1) <= 512,
+     * width + 1 <= 128, node rounds counted with 128.
      */
     int32_t grid_nx, grid_ny, grid_nz;
     int32_t n_footprints4, n_footprints2;
-    int32_t reserved;
+    int32_t n_footprints4h;
     const double *grid_xs;         /* [nx+1] node coordinates                   */
     const double *grid_ys;         /* [ny+1]                                    */
     const double *grid_zs;         /* [nz+1] ascending                          */
@@ -113,6 +117,7 @@ typedef struct {
     int64_t n_nodes;
     const double *node_xyz;        /* [3][n_nodes]                              */
     const int32_t *cell_nodes32;   /* [n_cells][8], F-order vertices            */
+    const int32_t *footprints4h;   /* [n_footprints4h][6] (see grid_nx above)   */
 } pf_plan;
 
 /*

@@ -15,7 +15,7 @@ import os
 LIB_PATH = Path(os.environ.get("PF_CUDA_LIB", Path(__file__).resolve().parent / "libpf_cuda.so"))
 
 PF_MAX_COMPONENTS = 16
-PF_ABI_VERSION = 5
+PF_ABI_VERSION = 6
 PF_F64, PF_F32 = 0, 1
 PF_GRAVITY, PF_MAGNETICS = 0, 1
 
@@ -64,11 +64,12 @@ class PfPlan(ctypes.Structure):
         ("tile_n_nodes", ctypes.c_void_p),
         ("grid_nx", ctypes.c_int32), ("grid_ny", ctypes.c_int32), ("grid_nz", ctypes.c_int32),
         ("n_footprints4", ctypes.c_int32), ("n_footprints2", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("n_footprints4h", ctypes.c_int32),
         ("grid_xs", ctypes.c_void_p), ("grid_ys", ctypes.c_void_p), ("grid_zs", ctypes.c_void_p),
         ("grid_colmap", ctypes.c_void_p),
         ("footprints4", ctypes.c_void_p), ("footprints2", ctypes.c_void_p),
         ("n_nodes", ctypes.c_int64), ("node_xyz", ctypes.c_void_p), ("cell_nodes32", ctypes.c_void_p),
+        ("footprints4h", ctypes.c_void_p),
     ]
 
 

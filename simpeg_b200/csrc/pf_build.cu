@@ -552,11 +552,11 @@ __device__ __forceinline__ int node_S_sign(double e, double n, double u)
     return zeros >= 2 ? 0 : (sb ? -1 : 1);
 }
 
-template <int FAM, int PROG, int SINK, typename GT, int NR>
-__global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
+template <int FAM, int PROG, int SINK, typename GT, int NR, int MT = PF_THREADS>
+__global__ void __launch_bounds__(MT, PF_MARCH_MIN_BLOCKS * (PF_THREADS / MT))
     pf_march_kernel(const __grid_constant__ LaunchParams p)
 {
-    constexpr int NCAP = NR * PF_THREADS;   // node slots per layer
+    constexpr int NCAP = NR * MT;   // node slots per layer
     constexpr int LAYER_BYTES = NCAP * 8;
     extern __shared__ double smem[];
     const int n_planes = p.n_planes;
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const int buf_doubles = n_planes * NCAP;
     const int n_buf = p.n_buf;    // 1 when two buffers would not leave room for 3 CTAs per SM
     double *dprev = smem + n_buf * (size_t)buf_doubles;       // [n_plain][NR][THREADS] corner differences
-    double *wacc = dprev + (size_t)n_plain * NR * PF_THREADS; // [WARPS][n_fwd] (forward)
+    double *wacc = dprev + (size_t)n_plain * NR * MT; // [(MT / 32)][n_fwd] (forward)
     // per-output bookkeeping, refreshed once per receiver: destination of column 0 of
     // the output's row/block (store) or of its model block (forward), its factor and role
     __shared__ unsigned long long s_dst[MAX_OUT];
@@ -577,7 +577,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     const unsigned smem32 = (unsigned)__cvta_generic_to_shared(smem);          // shared-window addresses
     const unsigned dprev32 = (unsigned)__cvta_generic_to_shared(dprev) + tid * 8;
     const int nx = p.plan.grid_nx, ny = p.plan.grid_ny;
-    const int32_t *fp = ((NR == 4) ? p.plan.footprints4 : p.plan.footprints2) + 6 * blockIdx.x;
+    const int32_t *fp = ((MT != PF_THREADS) ? p.plan.footprints4h
+                                            : ((NR == 4) ? p.plan.footprints4 : p.plan.footprints2)) + 6 * blockIdx.x;
     const int ix0 = fp[0], iy0 = fp[1], fw = fp[2], fh = fp[3];
     const int iz_begin = fp[4], iz_end = fp[5];   // cell layers that hold active cells
     const int W1 = fw + 1;
@@ -596,9 +597,9 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     // x for every node of the thread (e = x - rx is formed once per receiver and its square hoisted
     // out of the layer loop; the y of a round is one L1 load).  Footprints wider than THREADS - 1
     // cells are a plan error (include/pf_cuda.h; tiling.march_footprints never makes them).
-    if (W1 > PF_THREADS) __trap();
-    const int RW = (PF_THREADS / W1) * W1;            // node slots per round
-    const int rows_per_round = PF_THREADS / W1;
+    if (W1 > MT) __trap();
+    const int RW = (MT / W1) * W1;            // node slots per round
+    const int rows_per_round = MT / W1;
     const bool node_thread = tid < RW;
     const double xnode = __ldg(p.plan.grid_xs + ix0 + (node_thread ? tid % W1 : 0));
     const double *yrow = p.plan.grid_ys + iy0 + (node_thread ? tid / W1 : 0);
@@ -607,14 +608,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
     int cbase[NR];     // mesh index of the cell in layer 0, -1 = no cell in this slot
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
-        const int c = tid + s * PF_THREADS;
+        const int c = tid + s * MT;
         const int cy = c / fw, cx = c - cy * fw;
         const bool ok = c < n_layer_cells;
         o00[s] = (cx + W1 * cy) * 8;
         cbase[s] = ok ? (ix0 + cx) + nx * (iy0 + cy) : -1;
     }
     if (SINK == SINK_FORWARD) {
-        for (int i = tid; i < WARPS * p.n_fwd; i += PF_THREADS) wacc[i] = 0.0;
+        for (int i = tid; i < (MT / 32) * p.n_fwd; i += MT) wacc[i] = 0.0;
     }
     // closed (x, y) bounding box of the footprint's nodes (derived outputs only)
     double box_x0 = 0, box_x1 = 0, box_y0 = 0, box_y1 = 0;
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
         };
         // exact sum_v s_v S_v of the cell in slot s between node layers L-1 and L (rare path)
         auto cell_S = [&](int s, int L) -> double {
-            const int c = tid + s * PF_THREADS;
+            const int c = tid + s * MT;
             const int cy = c / fw, cx = c - cy * fw;
             const double e0 = __ldg(p.plan.grid_xs + ix0 + cx) - rx, e1 = __ldg(p.plan.grid_xs + ix0 + cx + 1) - rx;
             const double n0 = __ldg(p.plan.grid_ys + iy0 + cy) - ry, n1 = __ldg(p.plan.grid_ys + iy0 + cy + 1) - ry;
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 const double *mrow = reinterpret_cast<const double *>(s_dst[O]);                  \
                 const double factor = s_fac[O];                                                   \
                 const int role = s_role[O];                                                       \
-                double *dp = dprev + (size_t)(O) * (NR * PF_THREADS) + tid;                       \
+                double *dp = dprev + (size_t)(O) * (NR * MT) + tid;                       \
                 _Pragma("unroll") for (int s = 0; s < NR; ++s) {                                  \
                     if (cbase[s] < 0) continue;                                                   \
                     const char *q = pl + (POFF) + o00[s];                                         \
@@ -703,8 +704,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                                          - *reinterpret_cast<const double *>(q + 8)               \
                                          - *reinterpret_cast<const double *>(q + sW)              \
                                          + *reinterpret_cast<const double *>(q + sW + 8);         \
-                    const double d_old = dp[s * PF_THREADS];                                      \
-                    dp[s * PF_THREADS] = d_new;                                                   \
+                    const double d_old = dp[s * MT];                                      \
+                    dp[s * MT] = d_new;                                                   \
                     const double g = factor * (d_new - d_old);                                    \
                     if (role == ROLE_KEEP_A) keep_a[s] = g;                                       \
                     if (role == ROLE_KEEP_B) keep_b[s] = g;                                       \
@@ -793,14 +794,14 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                     if (O < NO) {                                                                     \
                         const double d_new = lds_f64<(O) * LAYER_BYTES>(q0) - lds_f64<(O) * LAYER_BYTES + 8>(q0) \
                                              - lds_f64<(O) * LAYER_BYTES>(q1) + lds_f64<(O) * LAYER_BYTES + 8>(q1); \
-                        const double d_old = (s == 0)   ? lds_f64<((O) * NR + 0) * PF_THREADS * 8>(dp32) \
-                                             : (s == 1) ? lds_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dp32) \
-                                             : (s == 2) ? lds_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dp32) \
-                                                        : lds_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dp32); \
-                        if (s == 0) sts_f64<((O) * NR + 0) * PF_THREADS * 8>(dp32, d_new);            \
-                        else if (s == 1) sts_f64<((O) * NR + 1 % NR) * PF_THREADS * 8>(dp32, d_new);  \
-                        else if (s == 2) sts_f64<((O) * NR + 2 % NR) * PF_THREADS * 8>(dp32, d_new);  \
-                        else sts_f64<((O) * NR + 3 % NR) * PF_THREADS * 8>(dp32, d_new);              \
+                        const double d_old = (s == 0)   ? lds_f64<((O) * NR + 0) * MT * 8>(dp32) \
+                                             : (s == 1) ? lds_f64<((O) * NR + 1 % NR) * MT * 8>(dp32) \
+                                             : (s == 2) ? lds_f64<((O) * NR + 2 % NR) * MT * 8>(dp32) \
+                                                        : lds_f64<((O) * NR + 3 % NR) * MT * 8>(dp32); \
+                        if (s == 0) sts_f64<((O) * NR + 0) * MT * 8>(dp32, d_new);            \
+                        else if (s == 1) sts_f64<((O) * NR + 1 % NR) * MT * 8>(dp32, d_new);  \
+                        else if (s == 2) sts_f64<((O) * NR + 2 % NR) * MT * 8>(dp32, d_new);  \
+                        else sts_f64<((O) * NR + 3 % NR) * MT * 8>(dp32, d_new);              \
                         const double g = PF_IS_TMI(PROG) ? (d_new - d_old) : factor * (d_new - d_old); \
                         if (SINK == SINK_STORE) {                                                     \
                             if (st) reinterpret_cast<GT *>(dst[(O) < NO ? (O) : 0])[cu] = (GT)g;      \
@@ -824,7 +825,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                 GT *grow = reinterpret_cast<GT *>(s_dst[O]);                                      \
                 const double *mrow = reinterpret_cast<const double *>(s_dst[O]);                  \
                 const double factor = s_fac[O];                                                   \
-                double *dp = dprev + (size_t)(O) * (NR * PF_THREADS) + tid;                       \
+                double *dp = dprev + (size_t)(O) * (NR * MT) + tid;                       \
                 _Pragma("unroll") for (int s = 0; s < NR; ++s) {                                  \
                     if (cbase[s] < 0) continue;                                                   \
                     const char *q = pl + (POFF) + o00[s];                                         \
@@ -832,8 +833,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
                                          - *reinterpret_cast<const double *>(q + 8)               \
                                          - *reinterpret_cast<const double *>(q + sW)              \
                                          + *reinterpret_cast<const double *>(q + sW + 8);         \
-                    const double d_old = dp[s * PF_THREADS];                                      \
-                    dp[s * PF_THREADS] = d_new;                                                   \
+                    const double d_old = dp[s * MT];                                      \
+                    dp[s * MT] = d_new;                                                   \
                     if (col[s] < 0) continue;                                                     \
                     const double g = factor * (d_new - d_old);                                    \
                     if (SINK == SINK_STORE) grow[(unsigned)col[s]] = (GT)g;                       \
@@ -885,7 +886,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MARCH_MIN_BLOCKS)
             if (tid < p.n_fwd) {
                 double t = 0.0;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) {
+                for (int w = 0; w < (MT / 32); ++w) {
                     t += wacc[w * p.n_fwd + tid];
                     wacc[w * p.n_fwd + tid] = 0.0;
                 }
@@ -1443,10 +1444,10 @@ int launch_pass(const Pass &pass, cudaStream_t stream)
 // ---- z-marching kernel dispatch (tensor meshes) --------------------------------
 constexpr size_t MARCH_SMEM_LIMIT = 110 * 1024;  // keeps >= 2 CTAs per SM
 
-size_t march_smem_n(const LaunchParams &p, int nr, bool forward, int n_buf)
+size_t march_smem_n(const LaunchParams &p, int nr, bool forward, int n_buf, int mt = PF_THREADS)
 {
-    return (((size_t)n_buf * p.n_planes + (p.n_out - p.n_derived)) * nr * PF_THREADS
-            + (forward ? WARPS * p.n_fwd : 0)) * sizeof(double);
+    return (((size_t)n_buf * p.n_planes + (p.n_out - p.n_derived)) * nr * mt
+            + (forward ? (mt / 32) * p.n_fwd : 0)) * sizeof(double);
 }
 
 // double-buffered node planes (one barrier per layer) unless that costs the third CTA per SM and
@@ -1455,16 +1456,17 @@ size_t march_smem_n(const LaunchParams &p, int nr, bool forward, int n_buf)
 #define PF_MARCH_SMEM_BUDGET (74 * 1024)
 #endif
 constexpr size_t MARCH_SMEM_3CTAS = PF_MARCH_SMEM_BUDGET;
-int march_buffers(const LaunchParams &p, int nr, bool forward)
+int march_buffers(const LaunchParams &p, int nr, bool forward, int mt = PF_THREADS)
 {
-    if (march_smem_n(p, nr, forward, 2) > MARCH_SMEM_3CTAS && march_smem_n(p, nr, forward, 1) <= MARCH_SMEM_3CTAS)
+    const size_t budget = MARCH_SMEM_3CTAS * mt / PF_THREADS;     // (6 CTAs per SM at 128 threads)
+    if (march_smem_n(p, nr, forward, 2, mt) > budget && march_smem_n(p, nr, forward, 1, mt) <= budget)
         return 1;
     return 2;
 }
 
-size_t march_smem(const LaunchParams &p, int nr, bool forward)
+size_t march_smem(const LaunchParams &p, int nr, bool forward, int mt = PF_THREADS)
 {
-    return march_smem_n(p, nr, forward, march_buffers(p, nr, forward));
+    return march_smem_n(p, nr, forward, march_buffers(p, nr, forward, mt), mt);
 }
 
 // node rounds per layer (4 -> 1024-node footprints, 2 -> 512) or 0 when the pass
@@ -1479,19 +1481,42 @@ int march_rounds(const pf_plan *plan, const LaunchParams &p, bool forward)
     return 0;
 }
 
-template <int FAM, int PROG, int SINK, typename GT, int NR>
+// Threads per CTA of a marching pass.  The three-plane vector program runs in 128-thread CTAs (six
+// per SM instead of three, 512-node footprints `footprints4h`) when the plan carries that set: a CTA
+// in its cell phase then takes a sixth instead of a third of the partition's warps off the FP64 pipe
+// (measured: build +1.5 %, blocked diagonal +7 %; the one-plane programs lose 1.5 % and keep 256).
+#ifndef PF_MARCH_HALF_CTAS
+#define PF_MARCH_HALF_CTAS 1
+#endif
+constexpr int MARCH_HALF_THREADS = 128;
+int march_threads(const pf_plan *plan, const Pass &pass, int nr)
+{
+    if (PF_MARCH_HALF_CTAS && pass.family == 12 && pass.prog == PROG_TMI_VECTOR && nr == 4 &&
+        plan->n_footprints4h > 0 && plan->footprints4h)
+        return MARCH_HALF_THREADS;
+    return PF_THREADS;
+}
+// footprints (= grid.x and forward partials) of a marching pass
+int march_parts(const pf_plan *plan, const Pass &pass, int nr)
+{
+    if (march_threads(plan, pass, nr) != PF_THREADS) return plan->n_footprints4h;
+    return (nr == 4) ? plan->n_footprints4 : plan->n_footprints2;
+}
+
+template <int FAM, int PROG, int SINK, typename GT, int NR, int MT = PF_THREADS>
 int launch_march_kernel(const LaunchParams &p, cudaStream_t stream)
 {
-    const size_t smem = march_smem(p, NR, SINK == SINK_FORWARD);
-    auto kernel = pf_march_kernel<FAM, PROG, SINK, GT, NR>;
+    const size_t smem = march_smem(p, NR, SINK == SINK_FORWARD, MT);
+    auto kernel = pf_march_kernel<FAM, PROG, SINK, GT, NR, MT>;
     LaunchParams q = p;
-    q.n_buf = march_buffers(p, NR, SINK == SINK_FORWARD);
+    q.n_buf = march_buffers(p, NR, SINK == SINK_FORWARD, MT);
     PF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunks = pf_ceil_div(p.n_receivers, p.rc);
     PF_CHECK_ARG(chunks <= 65535, "too many receiver chunks");
-    const int n_fp = (NR == 4) ? p.plan.n_footprints4 : p.plan.n_footprints2;
+    const int n_fp = (MT != PF_THREADS) ? p.plan.n_footprints4h
+                                        : ((NR == 4) ? p.plan.n_footprints4 : p.plan.n_footprints2);
     dim3 grid((unsigned)n_fp, (unsigned)chunks);
-    kernel<<<grid, PF_THREADS, smem, stream>>>(q);
+    kernel<<<grid, MT, smem, stream>>>(q);
     PF_COUNT_LAUNCH();
     PF_CUDA_OK(cudaGetLastError());
     return PF_OK;
@@ -1501,8 +1526,13 @@ template <int SINK, typename GT, int NR>
 int launch_march_nr(const Pass &pass, cudaStream_t stream)
 {
     if (pass.family == 12) {
-        if (pass.prog == PROG_TMI_VECTOR)
+        if (pass.prog == PROG_TMI_VECTOR) {
+            if constexpr (NR == 4) {
+                if (march_threads(&pass.p.plan, pass, NR) == MARCH_HALF_THREADS)
+                    return launch_march_kernel<12, PROG_TMI_VECTOR, SINK, GT, NR, MARCH_HALF_THREADS>(pass.p, stream);
+            }
             return launch_march_kernel<12, PROG_TMI_VECTOR, SINK, GT, NR>(pass.p, stream);
+        }
         if (pass.prog == PROG_TMI_SCALAR)
             return launch_march_kernel<12, PROG_TMI_SCALAR, SINK, GT, NR>(pass.p, stream);
         if (pass.prog == PROG_ALL6)
@@ -1545,6 +1575,7 @@ int validate_grid(const pf_plan *plan)
     PF_CHECK_ARG(plan->n_footprints4 >= 0 && plan->n_footprints2 >= 0, "negative footprint count");
     PF_CHECK_ARG(plan->n_footprints4 == 0 || plan->footprints4, "null footprints4");
     PF_CHECK_ARG(plan->n_footprints2 == 0 || plan->footprints2, "null footprints2");
+    PF_CHECK_ARG(plan->n_footprints4h >= 0 && (plan->n_footprints4h == 0 || plan->footprints4h), "bad footprints4h");
     PF_CHECK_ARG(plan->grid_colmap || (int64_t)plan->grid_nx * plan->grid_ny * plan->grid_nz == plan->n_cells,
                  "grid without colmap must have n_cells == nx ny nz");
     return PF_OK;
@@ -1593,7 +1624,7 @@ extern "C" int pf_build_G(const pf_plan *plan, const pf_job *job, void *G, int64
         p.ldG = ldG;
         const int nr = march_rounds(plan, p, false);
         if (nr) {
-            const int n_fp = (nr == 4) ? plan->n_footprints4 : plan->n_footprints2;
+            const int n_fp = march_parts(plan, passes[i], nr);
             p.rc = choose_rc(n_fp, job->n_receivers, 65535);
             st = (g_dtype == PF_F64) ? launch_march<SINK_STORE, double>(passes[i], nr, (cudaStream_t)stream)
                                      : launch_march<SINK_STORE, float>(passes[i], nr, (cudaStream_t)stream);
@@ -1620,6 +1651,7 @@ int64_t forward_parts(const pf_plan *plan)
     int64_t parts = plan->n_tiles;
     if (plan->n_footprints4 > parts) parts = plan->n_footprints4;
     if (plan->n_footprints2 > parts) parts = plan->n_footprints2;
+    if (plan->n_footprints4h > parts) parts = plan->n_footprints4h;
     return parts > 0 ? parts : 1;
 }
 
@@ -1682,7 +1714,7 @@ static int pf_forward_chunk(const pf_plan *plan, const pf_job *job, const double
         const int nr = march_rounds(plan, p, true);
         int64_t n_parts = plan->n_tiles;
         if (nr) {
-            n_parts = (nr == 4) ? plan->n_footprints4 : plan->n_footprints2;
+            n_parts = march_parts(plan, passes[i], nr);
             p.rc = choose_rc(n_parts, job->n_receivers, 65535);
             st = launch_march<SINK_FORWARD, double>(passes[i], nr, (cudaStream_t)stream);
         } else {
@@ -1946,14 +1978,23 @@ extern "C" int pf_describe(const pf_plan *plan, const pf_job *job, int sink, int
         char one[160];
         int nr = 0;
         if (sink == SINK_STORE || sink == SINK_FORWARD) nr = march_rounds(plan, p, sink == SINK_FORWARD);
-        if (nr)
+        if (nr && march_threads(plan, passes[i], nr) != PF_THREADS)
+            snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,%s,%s,%d,%d>", passes[i].family,
+                     prog_name(passes[i].prog), sink_name(sink), gt, nr, march_threads(plan, passes[i], nr));
+        else if (nr)
             snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,%s,%s,%d>", passes[i].family,
                      prog_name(passes[i].prog), sink_name(sink), gt, nr);
         else if (sink == SINK_GTV && plan->n_nodes > 0)
             snprintf(one, sizeof(one), "pf_node_gtv_kernel<%d,%s>", passes[i].family, prog_name(passes[i].prog));
-        else if (sink == SINK_DIAG && blocked_diag)
-            snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,SINK_STORE,double,%d> + column_kernel<double,1>",
-                     passes[i].family, prog_name(passes[i].prog), march_rounds(plan, p, false));
+        else if (sink == SINK_DIAG && blocked_diag) {
+            const int nrd = march_rounds(plan, p, false), mtd = march_threads(plan, passes[i], nrd);
+            if (mtd != PF_THREADS)
+                snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,SINK_STORE,double,%d,%d> + column_kernel<double,1>",
+                         passes[i].family, prog_name(passes[i].prog), nrd, mtd);
+            else
+                snprintf(one, sizeof(one), "pf_march_kernel<%d,%s,SINK_STORE,double,%d> + column_kernel<double,1>",
+                         passes[i].family, prog_name(passes[i].prog), nrd);
+        }
         else
             snprintf(one, sizeof(one), "pf_tile_kernel<%d,%s,%s,%s>", passes[i].family,
                      prog_name(passes[i].prog), sink_name(sink), gt);

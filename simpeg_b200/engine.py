@@ -89,6 +89,8 @@ class CudaEngine:
                     torch.from_numpy(hp.grid_colmap).to(self.device)
                 self._t_fp4 = torch.from_numpy(hp.footprints4).to(self.device)
                 self._t_fp2 = torch.from_numpy(hp.footprints2).to(self.device)
+                fp4h = getattr(hp, "footprints4h", None)
+                self._t_fp4h = None if fp4h is None or fp4h.shape[0] == 0 else torch.from_numpy(fp4h).to(self.device)
             self.plan.grid_nx, self.plan.grid_ny, self.plan.grid_nz = hp.grid_shape
             self.plan.grid_xs, self.plan.grid_ys, self.plan.grid_zs = (t.data_ptr() for t in self._t_axes)
             self.plan.grid_colmap = None if self._t_colmap is None else self._t_colmap.data_ptr()
@@ -96,6 +98,8 @@ class CudaEngine:
             self.plan.n_footprints2 = hp.footprints2.shape[0]
             self.plan.footprints4 = self._t_fp4.data_ptr() if hp.footprints4.shape[0] else None
             self.plan.footprints2 = self._t_fp2.data_ptr() if hp.footprints2.shape[0] else None
+            self.plan.n_footprints4h = 0 if self._t_fp4h is None else self._t_fp4h.shape[0]
+            self.plan.footprints4h = None if self._t_fp4h is None else self._t_fp4h.data_ptr()
 
         table = _lib.GRAVITY_COMPONENTS if physics == "gravity" else _lib.MAGNETIC_COMPONENTS
         code = _lib.PF_GRAVITY if physics == "gravity" else _lib.PF_MAGNETICS

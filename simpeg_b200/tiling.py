@@ -32,6 +32,7 @@ import numpy as np
 TILE_CELLS = 512
 TILE_NODES = 768
 _ROUND = 256  # threads per CTA: cost is paid per round of 256 nodes / cells
+_MARCH_HALF = 128  # threads per CTA of the half-size variant of the z-marching kernel (footprints4h)
 
 
 @dataclass
@@ -51,6 +52,7 @@ class TilePlan:
     grid_colmap: np.ndarray | None = None  # (nx*ny*nz,) int32, None = all active
     footprints4: np.ndarray | None = None  # (n, 6) int32
     footprints2: np.ndarray | None = None
+    footprints4h: np.ndarray | None = None  # <= 512 nodes, for 128-thread CTAs (three-plane programs)
     active_index: np.ndarray | None = None  # tensor meshes: mesh indices of the active cells
     # generic plans keep the (nodes, cell_nodes) they were built from
     nodes: np.ndarray | None = None
@@ -293,11 +295,19 @@ def build_tile_plan_tensor(axis_nodes, active_index=None, with_tiles=True) -> Ti
             for sz, cz in _axis_parts(nz, bz):
                 brick_slots += cx * cy * cz * (-(-((sx + 1) * (sy + 1) * (sz + 1)) // _ROUND) * _ROUND)
     # keep a footprint set only if it evaluates fewer node slots per cell than the bricks
-    for name, ncap in (("footprints4", 1024), ("footprints2", 512)):
-        fps = march_footprints(nx, ny, nz, ncap, act)
-        rounds = march_node_rounds(fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64))
-        slots = float(((rounds * _ROUND) * (fps[:, 5] - fps[:, 4] + 1)).sum())
+    for name, ncap, threads in (("footprints4", 1024, _ROUND), ("footprints2", 512, _ROUND),
+                                ("footprints4h", 4 * _MARCH_HALF, _MARCH_HALF)):
+        fps = march_footprints(nx, ny, nz, ncap, act, threads)
+        rounds = march_node_rounds(fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64), threads)
+        slots = float(((rounds * threads) * (fps[:, 5] - fps[:, 4] + 1)).sum())
         setattr(plan, name, fps if slots < 0.95 * brick_slots else np.zeros((0, 6), np.int32))
+    # the half-size set only pays when it evaluates no more node slots than the full-size one
+    if plan.footprints4.shape[0] and plan.footprints4h.shape[0]:
+        def total(fps, threads):
+            r = march_node_rounds(fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64), threads)
+            return float(((r * threads) * (fps[:, 5] - fps[:, 4] + 1)).sum())
+        if total(plan.footprints4h, _MARCH_HALF) > 1.02 * total(plan.footprints4, _ROUND):
+            plan.footprints4h = np.zeros((0, 6), np.int32)
     if with_tiles:
         plan.ensure_tiles()
     return plan
@@ -308,22 +318,23 @@ def _axis_parts(d, b):
     return [(b, full)] + ([(rem, 1)] if rem else [])
 
 
-def march_node_rounds(w, h):
-    """256-thread node rounds per layer of a w x h-cell footprint (whole node rows per round)."""
-    rows = np.maximum(_ROUND // (np.asarray(w) + 1), 1)
+def march_node_rounds(w, h, threads=_ROUND):
+    """Node rounds per layer of a w x h-cell footprint (whole node rows per round of `threads`)."""
+    rows = np.maximum(threads // (np.asarray(w) + 1), 1)
     return -(-(np.asarray(h) + 1) // rows)
 
 
-def march_footprints(nx, ny, nz, ncap, active_index=None):
+def march_footprints(nx, ny, nz, ncap, active_index=None, threads=_ROUND):
     """
     (x, y) footprints for the z-marching kernel: an a x b grid of rectangles,
-    each with (w + 1)(h + 1) <= ncap nodes per layer and w + 1 <= 256, chosen to
-    minimise the number of 256-thread node rounds per layer; rows are
+    each with (w + 1)(h + 1) <= ncap nodes per layer and w + 1 <= threads, chosen to
+    minimise the number of node rounds per layer (threads = 256, or 128 for the
+    half-size CTAs of the three-plane programs); rows are
     (ix0, iy0, w, h, iz_begin, iz_end).
 
-    The kernel takes a layer's nodes floor(256 / (w + 1)) whole rows per round
+    The kernel takes a layer's nodes floor(threads / (w + 1)) whole rows per round
     (a thread keeps one node column, csrc/pf_build.cu), so a footprint costs
-    ceil((h + 1) / floor(256 / (w + 1))) node rounds.
+    ceil((h + 1) / floor(threads / (w + 1))) node rounds.
     """
     # every (a, b) split (this runs inside every simulation's first G access): one numpy pass over
     # the whole (a, b) table for ordinary meshes, row blocks of it for huge ones (bounded memory)
@@ -335,9 +346,9 @@ def march_footprints(nx, ny, nz, ncap, active_index=None):
         a_blk = np.arange(a0, min(a0 + rows_per_block, nx + 1), dtype=np.int64)[:, None]
         w_blk = -(-nx // a_blk)
         nodes_all = (w_blk + 1) * (h_all + 1)
-        rounds_all = march_node_rounds(w_blk, h_all)
-        cost = (a_blk * b_all * (4 * rounds_all + -(-(w_blk * h_all) // _ROUND))).astype(np.float64)
-        cost[(nodes_all > ncap) | ((w_blk + 1) * 2 > ncap) | (w_blk + 1 > _ROUND)] = np.inf
+        rounds_all = march_node_rounds(w_blk, h_all, threads)
+        cost = (a_blk * b_all * (4 * rounds_all + -(-(w_blk * h_all) // threads))).astype(np.float64)
+        cost[(nodes_all > ncap) | ((w_blk + 1) * 2 > ncap) | (w_blk + 1 > threads)] = np.inf
         flat = int(np.argmin(cost))            # row-major: smallest a, then smallest b, among equals
         c = float(cost.flat[flat])
         if np.isfinite(c) and (best is None or c < best[0]):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_struct_layout():
     lib = _lib.load_library()
     assert lib.pf_abi_version() == _lib.PF_ABI_VERSION
-    assert ctypes.sizeof(_lib.PfPlan) == 152
+    assert ctypes.sizeof(_lib.PfPlan) == 160
     assert ctypes.sizeof(_lib.PfJob) == 128
 
 

@@ -186,10 +186,12 @@ def test_marching_kernel_footprint_shapes(shape):
     # the planner drops footprint sets that are no better than bricks on such meshes: force them
     plan.footprints4 = march_footprints(*shape, 1024)
     plan.footprints2 = march_footprints(*shape, 512)
+    plan.footprints4h = march_footprints(*shape, 512, threads=128)     # 128-thread CTAs (TMI vector)
     for physics, comps, mt in (("magnetics", ["tmi"], "vector"),
                                ("gravity", ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz", "gz"], "scalar")):
         eng = CudaEngine(physics, None, None, [(loc, comps)], b0=B0, model_type=mt, plan=plan, use_marching=True)
         assert eng.plan.grid_nx == shape[0] and "pf_march_kernel" in eng.describe("store")
+        assert eng.describe("store").endswith(",4,128>") == (mt == "vector")
         ora = OracleSimulation(physics, mesh.nodes, mesh.cell_nodes, [(loc, comps)], b0=B0, model_type=mt)
         G_ref = ora.sensitivity_matrix()
         eng.build_G()

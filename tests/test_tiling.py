@@ -116,14 +116,30 @@ def test_march_footprints_cover_the_mesh_within_the_kernel_limits(shape):
     from simpeg_b200.tiling import march_footprints, march_node_rounds
 
     nx, ny, nz = shape
-    for ncap in (1024, 512):
-        fps = march_footprints(nx, ny, nz, ncap)
+    for ncap, threads in ((1024, 256), (512, 256), (512, 128)):
+        fps = march_footprints(nx, ny, nz, ncap, threads=threads)
         cover = np.zeros((nx, ny), dtype=int)
         for ix0, iy0, w, h, z0, z1 in fps:
-            assert (w + 1) * (h + 1) <= ncap and w + 1 <= 256 and w >= 1 - (nx == 1) and h >= 1 - (ny == 1)
+            assert (w + 1) * (h + 1) <= ncap and w + 1 <= threads and w >= 1 - (nx == 1) and h >= 1 - (ny == 1)
             assert (z0, z1) == (0, nz)
             cover[ix0:ix0 + w, iy0:iy0 + h] += 1
         assert (cover == 1).all()
         # the node-round count the planner minimises is the kernel's: whole rows per round
         w, h = fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64)
-        assert np.array_equal(march_node_rounds(w, h), -(-(h + 1) // (256 // (w + 1))))
+        assert np.array_equal(march_node_rounds(w, h, threads), -(-(h + 1) // (threads // (w + 1))))
+
+
+def test_half_size_footprints_only_when_they_cost_no_more():
+    """The plan carries the set for 128-thread CTAs (footprints4h) only when it evaluates at most 2 %
+    more node slots per layer than the 256-thread set."""
+    from simpeg_b200.tiling import build_tile_plan_tensor, march_node_rounds
+
+    for shape in [(100, 100, 10), (200, 200, 10), (40, 40, 20), (130, 97, 5)]:
+        plan = build_tile_plan_tensor([np.arange(n + 1, dtype=float) for n in shape], None, with_tiles=False)
+        if plan.footprints4h.shape[0] == 0:
+            continue
+        def slots(fps, t):
+            return (march_node_rounds(fps[:, 2].astype(np.int64), fps[:, 3].astype(np.int64), t) * t).sum()
+        assert slots(plan.footprints4h, 128) <= 1.02 * slots(plan.footprints4, 256)
+        assert (plan.footprints4h[:, 2] + 1 <= 128).all()
+        assert ((plan.footprints4h[:, 2] + 1) * (plan.footprints4h[:, 3] + 1) <= 512).all()
