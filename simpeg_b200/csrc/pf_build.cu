@@ -263,8 +263,29 @@ __device__ __forceinline__ void eval_raw(int need, double e, double n, double u,
     }
 }
 
+// choclo.prism.kernel_e / kernel_n / kernel_u by cyclic symmetry: for the axis a with the other two
+// coordinates (b, c) in the reference's order
+//     k_a = -(b log(c + r) + c log(b + r) - a atan(b c / (a r)))
+// (kernel_u: a = u, b = e, c = n; kernel_e: a = e, b = n, c = u; kernel_n: a = n, b = u, c = e)
+template <int AXIS>
+__device__ __forceinline__ double g1_value(double e, double n, double u)
+{
+    const double a = (AXIS == 0) ? e : ((AXIS == 1) ? n : u);
+    const double b = (AXIS == 0) ? n : ((AXIS == 1) ? u : e);
+    const double c = (AXIS == 0) ? u : ((AXIS == 1) ? e : n);
+    const double r2 = e * e + n * n + u * u;
+    const bool r_is_zero = r2 == 0.0;
+    const double r = pf_sqrt(r2, r_is_zero);
+    double A, Lc, Lb;
+    pf_node_atan1_log2(a, b, c, r, r_is_zero, A, Lc, Lb);
+    return -(b * Lc + c * Lb - a * A);
+}
+
 // Evaluate the output planes of one (receiver, node) pair.
-template <int FAM, int PROG, int STRIDE>
+// G1_SPLIT: one straight-line copy of the PROG_G1 evaluation per axis (marching and node-space
+// kernels); the tile kernel, which keeps 16 vertex offsets live across its node loop, spills with
+// three copies and keeps the single copy with a run-time axis.
+template <int FAM, int PROG, int STRIDE, bool G1_SPLIT = true>
 __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, double n, double u,
                                           double *planes, int j)
 {
@@ -291,20 +312,26 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
         return;
     }
     if (PROG == PROG_G1) {
-        // choclo.prism.kernel_e / kernel_n / kernel_u by cyclic symmetry: for the axis a with the
-        // other two coordinates (b, c) in the reference's order
-        //     k_a = -(b log(c + r) + c log(b + r) - a atan(b c / (a r)))
-        // (kernel_u: a = u, b = e, c = n; kernel_e: a = e, b = n, c = u; kernel_n: a = n, b = u, c = e)
+        // one straight-line copy per axis behind a uniform branch: with a run-time axis the (a, b, c)
+        // selection cost 18 register moves per node and hid the squares shared with r^2
         const int axis = p.g1_axis;
-        const double a = (axis == 0) ? e : ((axis == 1) ? n : u);
-        const double b = (axis == 0) ? n : ((axis == 1) ? u : e);
-        const double c = (axis == 0) ? u : ((axis == 1) ? e : n);
-        const double r2 = e * e + n * n + u * u;
-        const bool r_is_zero = r2 == 0.0;
-        const double r = pf_sqrt(r2, r_is_zero);
-        double A, Lc, Lb;
-        pf_node_atan1_log2(a, b, c, r, r_is_zero, A, Lc, Lb);
-        planes[j] = -(b * Lc + c * Lb - a * A);
+        double v;
+        if (G1_SPLIT) {
+            if (axis == 2) v = g1_value<2>(e, n, u);
+            else if (axis == 0) v = g1_value<0>(e, n, u);
+            else v = g1_value<1>(e, n, u);
+        } else {
+            const double a = (axis == 0) ? e : ((axis == 1) ? n : u);
+            const double b = (axis == 0) ? n : ((axis == 1) ? u : e);
+            const double c = (axis == 0) ? u : ((axis == 1) ? e : n);
+            const double r2 = e * e + n * n + u * u;
+            const bool r_is_zero = r2 == 0.0;
+            const double r = pf_sqrt(r2, r_is_zero);
+            double A, Lc, Lb;
+            pf_node_atan1_log2(a, b, c, r, r_is_zero, A, Lc, Lb);
+            v = -(b * Lc + c * Lb - a * A);
+        }
+        planes[j] = v;
         return;
     }
     eval_raw<FAM>((PROG == PROG_ALL6) ? (NEED_AEE | NEED_ANN | NEED_AUU | NEED_LEN | NEED_LEU | NEED_LNU) : p.need,
@@ -418,7 +445,7 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
         // ---- phase 1: output planes of the tile nodes -> shared memory -------
 #pragma unroll 1
         for (int j = tid; j < nn; j += PF_THREADS)
-            eval_node<FAM, PROG, PF_TILE_NODES>(p, sxyz[j] - rx, sxyz[PF_TILE_NODES + j] - ry,
+            eval_node<FAM, PROG, PF_TILE_NODES, false>(p, sxyz[j] - rx, sxyz[PF_TILE_NODES + j] - ry,
                                                 sxyz[2 * PF_TILE_NODES + j] - rz, planes, j);
         __syncthreads();
 
