@@ -779,6 +779,7 @@ __global__ void __launch_bounds__(MT, PF_MARCH_MIN_BLOCKS * (PF_THREADS / MT))
             }
         };
         // ---- phase 2: corner differences of layer L; emits the cells between L-1 and L ----
+        double fsum_rx = 0.0;    // forward sink of the fixed-output programs: sum over the receiver's layers
         auto phase2 = [&](int L, const double *planes) {
             const char *pl = reinterpret_cast<const char *>(planes);
             const bool emit = L > iz_begin;
@@ -797,6 +798,7 @@ __global__ void __launch_bounds__(MT, PF_MARCH_MIN_BLOCKS * (PF_THREADS / MT))
             }
             double fsum = 0.0;
             if constexpr (PF_FIXED(PROG)) {
+                if (SINK == SINK_FORWARD) fsum = fsum_rx;     // one accumulator per thread and receiver
                 // one component, PF_NOUT outputs = planes = column blocks, one factor.  Slot-major; the
                 // <= 3 row pointers and the factor are read once per layer, so that an output costs
                 // 5 shared loads, 1 shared store, 5 FP64 and a 2-instruction global store
@@ -841,10 +843,8 @@ __global__ void __launch_bounds__(MT, PF_MARCH_MIN_BLOCKS * (PF_THREADS / MT))
                     PF_FIXED_OUT(2)
 #undef PF_FIXED_OUT
                 }
-                if (SINK == SINK_FORWARD && emit) {
-                    fsum = warp_sum(fsum);
-                    if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd] += fsum;
-                }
+                // (the warp reduction happens once per receiver, after the last layer)
+                if (SINK == SINK_FORWARD) fsum_rx = fsum;
                 return;
             }
 #define PF_PHASE2_BODY(O, POFF)                                                                   \
@@ -907,6 +907,10 @@ __global__ void __launch_bounds__(MT, PF_MARCH_MIN_BLOCKS * (PF_THREADS / MT))
             else phase2(L, planes);
 #endif
             if (n_buf == 1) __syncthreads();
+        }
+        if (SINK == SINK_FORWARD && PF_FIXED(PROG)) {
+            fsum_rx = warp_sum(fsum_rx);
+            if ((tid & 31) == 0) wacc[(tid >> 5) * p.n_fwd] += fsum_rx;
         }
         __syncthreads();   // all warps done with the last layer (buffers, dprev and wacc are reused)
         if (SINK == SINK_FORWARD) {
