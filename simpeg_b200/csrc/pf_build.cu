@@ -965,6 +965,20 @@ __global__ void __launch_bounds__(PF_THREADS, 3)
         const double rx = __ldg(p.receivers + 3 * r);
         const double ry = __ldg(p.receivers + 3 * r + 1);
         const double rz = __ldg(p.receivers + 3 * r + 2);
+        if constexpr (PF_FIXED(PROG)) {
+            // one component: one row, one coefficient per receiver; the <= 3 plane values stay in
+            // registers (no shared-memory round trip, no per-output descriptor reads)
+            const int64_t row = p.row_offset + r * p.n_comp_total + p.outs[0].ci;
+            const double coef = __ldg(p.vec + row) * p.outs[0].factor;
+            double loc[3] = {0.0, 0.0, 0.0};
+            eval_node<FAM, PROG, 1>(p, x - rx, y - ry, z - rz, loc, 0);
+            { const double yk = coef * loc[0] - c0, t = a0 + yk; c0 = (t - a0) - yk; a0 = t; }
+            if (PF_NOUT(PROG) == 3) {
+                { const double yk = coef * loc[1] - c1, t = a1 + yk; c1 = (t - a1) - yk; a1 = t; }
+                { const double yk = coef * loc[2] - c2, t = a2 + yk; c2 = (t - a2) - yk; a2 = t; }
+            }
+            continue;
+        }
         eval_node<FAM, PROG, PF_THREADS>(p, x - rx, y - ry, z - rz, vals, tid);
         for (int o = 0; o < n_out; ++o) {
             const OutDesc &od = p.outs[o];
