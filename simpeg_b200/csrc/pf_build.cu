@@ -282,10 +282,11 @@ __device__ __forceinline__ double g1_value(double e, double n, double u)
 }
 
 // Evaluate the output planes of one (receiver, node) pair.
-// G1_SPLIT: one straight-line copy of the PROG_G1 evaluation per axis (marching and node-space
-// kernels); the tile kernel, which keeps 16 vertex offsets live across its node loop, spills with
-// three copies and keeps the single copy with a run-time axis.
-template <int FAM, int PROG, int STRIDE, bool G1_SPLIT = true>
+// G1_AXIS: PROG_G1 evaluates one straight-line copy per axis; -1 = pick the copy here behind a
+// uniform branch (marching and node-space kernels), >= 0 = the caller's loop is already specialised
+// (the tile kernel, which keeps 16 vertex offsets live across its node loop and spills when the three
+// copies sit inside one loop, runs one of three loops).
+template <int FAM, int PROG, int STRIDE, int G1_AXIS = -1>
 __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, double n, double u,
                                           double *planes, int j)
 {
@@ -314,22 +315,14 @@ __device__ __forceinline__ void eval_node(const LaunchParams &p, double e, doubl
     if (PROG == PROG_G1) {
         // one straight-line copy per axis behind a uniform branch: with a run-time axis the (a, b, c)
         // selection cost 18 register moves per node and hid the squares shared with r^2
-        const int axis = p.g1_axis;
         double v;
-        if (G1_SPLIT) {
+        if (G1_AXIS >= 0) {
+            v = g1_value<(G1_AXIS >= 0 ? G1_AXIS : 0)>(e, n, u);     // the caller hoisted the branch
+        } else {
+            const int axis = p.g1_axis;
             if (axis == 2) v = g1_value<2>(e, n, u);
             else if (axis == 0) v = g1_value<0>(e, n, u);
             else v = g1_value<1>(e, n, u);
-        } else {
-            const double a = (axis == 0) ? e : ((axis == 1) ? n : u);
-            const double b = (axis == 0) ? n : ((axis == 1) ? u : e);
-            const double c = (axis == 0) ? u : ((axis == 1) ? e : n);
-            const double r2 = e * e + n * n + u * u;
-            const bool r_is_zero = r2 == 0.0;
-            const double r = pf_sqrt(r2, r_is_zero);
-            double A, Lc, Lb;
-            pf_node_atan1_log2(a, b, c, r, r_is_zero, A, Lc, Lb);
-            v = -(b * Lc + c * Lb - a * A);
         }
         planes[j] = v;
         return;
@@ -443,10 +436,22 @@ __global__ void __launch_bounds__(PF_THREADS, PF_MIN_BLOCKS) pf_tile_kernel(cons
         const double rz = __ldg(p.receivers + 3 * r + 2);
 
         // ---- phase 1: output planes of the tile nodes -> shared memory -------
+        if constexpr (PROG == PROG_G1) {
+            const int axis = p.g1_axis;
+#define PF_TILE_NODE_LOOP(AX)                                                                          \
+            _Pragma("unroll 1") for (int j = tid; j < nn; j += PF_THREADS)                           \
+                eval_node<FAM, PROG, PF_TILE_NODES, AX>(p, sxyz[j] - rx, sxyz[PF_TILE_NODES + j] - ry, \
+                                                        sxyz[2 * PF_TILE_NODES + j] - rz, planes, j);
+            if (axis == 2) { PF_TILE_NODE_LOOP(2) }
+            else if (axis == 0) { PF_TILE_NODE_LOOP(0) }
+            else { PF_TILE_NODE_LOOP(1) }
+#undef PF_TILE_NODE_LOOP
+        } else {
 #pragma unroll 1
-        for (int j = tid; j < nn; j += PF_THREADS)
-            eval_node<FAM, PROG, PF_TILE_NODES, false>(p, sxyz[j] - rx, sxyz[PF_TILE_NODES + j] - ry,
-                                                sxyz[2 * PF_TILE_NODES + j] - rz, planes, j);
+            for (int j = tid; j < nn; j += PF_THREADS)
+                eval_node<FAM, PROG, PF_TILE_NODES>(p, sxyz[j] - rx, sxyz[PF_TILE_NODES + j] - ry,
+                                                    sxyz[2 * PF_TILE_NODES + j] - rz, planes, j);
+        }
         __syncthreads();
 
         // ---- phase 2: cells ---------------------------------------------------
