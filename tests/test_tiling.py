@@ -64,11 +64,27 @@ def test_octree_with_hanging_nodes():
     assert len(widths) == 3              # three refinement levels present
     check_plan(mesh.total_nodes, mesh.cell_nodes)
     native = check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb")
-    # the native planner (csrc/pf_plan.cu) follows the same bisection rule as the numpy statement
-    # of it: same tiles (up to numbering), hence the same number of node evaluations
+    # the native planner (csrc/pf_plan.cu) cuts where a whole number of expected tiles fits on either
+    # side, the numpy statement of the bisection at the median: both are valid plans (check_plan), and
+    # the native one must not cost more 256-thread rounds (4 per node round, 1 per cell round)
     numpy_plan = check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb_numpy")
-    assert native.n_tiles == numpy_plan.n_tiles
-    assert native.node_evaluations == numpy_plan.node_evaluations
+
+    def rounds(plan):
+        cells = (plan.tile_cell_col >= 0).sum(axis=1)
+        return 4 * np.ceil(plan.tile_n_nodes / 256).sum() + np.ceil(cells / 256).sum()
+
+    assert rounds(native) <= 1.03 * rounds(numpy_plan)
+
+
+def test_native_planner_fills_tiles_on_a_large_octree():
+    """The proportional split of the native planner: on an octree with hanging nodes the tiles hold
+    clearly more cells than median bisection leaves them (which costs the same rounds per tile)."""
+    topo = lambda x, y: 50.0 * np.exp(-0.5 * ((x / 100.0) ** 2 + (y / 100.0) ** 2)) - 50.0  # noqa: E731
+    mesh = synthetic_octree((40, 40, 12), 10.0, levels=3, topo=topo)
+    plan = check_plan(mesh.total_nodes, mesh.cell_nodes, "rcb")
+    cells = (plan.tile_cell_col >= 0).sum(axis=1)
+    assert plan.tile_n_nodes.mean() >= 0.74 * TILE_NODES          # median bisection: ~0.69
+    assert cells.mean() >= 340
 
 
 def _check_tensor_plan(mesh, active=None):
